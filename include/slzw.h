@@ -1,0 +1,178 @@
+/*
+ * slzw.h -- C ABI of the B200-native batched LZW codec (salzweg-compatible).
+ *
+ * This is the drop-in boundary for the hot path of redwarp/lzw (crate `salzweg`):
+ * the GIF-style, TIFF-style and fixed-12-bit LZW encoders and decoders.  The
+ * reference has no FFI of its own; its boundary is the public Rust API
+ *   lzw/src/encoder.rs:199-220, 262-271  VariableEncoder::{encode, encode_to_vec}
+ *   lzw/src/encoder.rs:392-399, 435-439  GifStyleEncoder::{encode, encode_to_vec}
+ *   lzw/src/encoder.rs:479-487, 519-523  TiffStyleEncoder::{encode, encode_to_vec}
+ *   lzw/src/encoder.rs:565-576, 609-616  FixedEncoder::{encode, encode_to_vec}
+ *   lzw/src/decoder.rs:99-120, 163-172   VariableDecoder::{decode, decode_to_vec}
+ *   lzw/src/decoder.rs:333-340, 378-382  GifStyleDecoder::{decode, decode_to_vec}
+ *   lzw/src/decoder.rs:420-428, 460-464  TiffStyleDecoder::{decode, decode_to_vec}
+ *   lzw/src/decoder.rs:503-514, 544-551  FixedDecoder::{decode, decode_to_vec}
+ * Every entry point below says which of those it backs.  A Rust `salzweg`-shaped
+ * crate binds exactly these symbols (see INTEGRATION.md and bindings/rust/).
+ *
+ * All pointers are plain memory, all sizes are bytes, no C++/torch types cross
+ * this boundary.  Functions return SLZW_RC_* (launch-level result); per-stream
+ * results are reported through status[]/detail[]/out_len[] and mirror the
+ * reference's error enums (lzw/src/encoder.rs:16-29, lzw/src/decoder.rs:15-25).
+ *
+ * There is no CPU fallback: every entry point that moves data runs CUDA kernels
+ * on an sm_100a device and fails with SLZW_RC_NO_DEVICE / SLZW_RC_CUDA otherwise.
+ */
+#ifndef SLZW_H
+#define SLZW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLZW_VERSION_MAJOR 0
+#define SLZW_VERSION_MINOR 1
+
+/* ---- per-stream result codes (mirror salzweg's error enums) ------------------------- */
+typedef enum slzw_status {
+    SLZW_OK = 0,
+    /* EncodingError::CodeSize(cs) / DecodingError::CodeSize(cs); detail = cs.
+     * (encoder.rs:281-283, decoder.rs:180-182) */
+    SLZW_ERR_CODE_SIZE = 1,
+    /* EncodingError::UnexpectedCode{code, code_size}: detail = offending input byte
+     * (encoder.rs:315-317).  DecodingError::UnexpectedCode(code): detail = code
+     * (decoder.rs:241-243, 258-260, 599-601, 616-618). */
+    SLZW_ERR_UNEXPECTED_CODE = 2,
+    /* DecodingError::MissingClearCode (decoder.rs:281-283). */
+    SLZW_ERR_MISSING_CLEAR_CODE = 3,
+    /* DecodingError::Io(UnexpectedEof): input ended before the end-of-information
+     * code (io.rs:45, 115 via decoder.rs:220). */
+    SLZW_ERR_IO_UNEXPECTED_EOF = 4,
+    /* {Encoding,Decoding}Error::Io(WriteZero): the output slot is full; it behaves
+     * like the `&mut [u8]` writer the reference's benches use
+     * (benches/compare_crates.rs:65-77; io.rs:244, 307; decoder.rs:231, 270). */
+    SLZW_ERR_IO_WRITE_ZERO = 5,
+    /* The reference would panic (index out of bounds) on this input: encoder first
+     * byte >= 2^cs+2 followed by more data (encoder.rs:99, 311), or a decoder word
+     * longer than its 4091-byte stack (decoder.rs:247, 262).  out_len = bytes the
+     * reference had written before panicking. */
+    SLZW_ERR_REFERENCE_PANIC = 6
+} slzw_status;
+
+/* ---- function-level return codes ----------------------------------------------------- */
+typedef enum slzw_rc {
+    SLZW_RC_OK = 0,
+    SLZW_RC_CUDA = -1,        /* a CUDA call failed; see slzw_last_error() */
+    SLZW_RC_INVALID = -2,     /* bad argument (null pointer, bad flavour, ...) */
+    SLZW_RC_NO_DEVICE = -3,   /* no usable sm_100 CUDA device */
+    SLZW_RC_NOMEM = -4
+} slzw_rc;
+
+/* ---- codec options ---------------------------------------------------------------------
+ * flavour 0 = variable-width codes with clear/EOI (VariableEncoder/Decoder,
+ *             encoder.rs:273-346, decoder.rs:174-290)
+ * flavour 1 = fixed 12-bit codes, no control codes (FixedEncoder/Decoder,
+ *             encoder.rs:618-658, decoder.rs:553-642)
+ * code_size          2..=8, ignored by flavour 1
+ * big_endian         0 = Endianness::LittleEndian (LSB-first), 1 = BigEndian (MSB-first)
+ * tiff_early_change  0 = CodeSizeStrategy::Default, 1 = CodeSizeStrategy::Tiff
+ *                    (lib.rs:71-91), ignored by flavour 1
+ * Presets: GIF = {0, cs, 0, 0} (encoder.rs:392-399); TIFF = {0, 8, 1, 1}
+ * (encoder.rs:479-487); Fixed = {1, 0, le|be, 0} (encoder.rs:565-576). */
+typedef struct slzw_params {
+    uint8_t flavour;
+    uint8_t code_size;
+    uint8_t big_endian;
+    uint8_t tiff_early_change;
+} slzw_params;
+
+#define SLZW_FLAVOUR_VARIABLE 0
+#define SLZW_FLAVOUR_FIXED 1
+
+/* ---- a batch of independent streams -----------------------------------------------------
+ * Stream i reads in[in_off[i] .. in_off[i+1]) and may write out[out_off[i] .. out_off[i+1])
+ * (its capacity slot, the analogue of the reference's `&mut [u8]` writer).  On return
+ *   out_len[i] = bytes produced (including those produced before an error),
+ *   status[i]  = slzw_status, detail[i] = see slzw_status.
+ * code_size (optional, may be NULL) overrides params.code_size per stream (GIF frames of
+ * different palettes in one batch).  For the *_device entry points every pointer is a device
+ * pointer; for the *_host entry points every pointer is a host pointer. */
+typedef struct slzw_batch {
+    const uint8_t* in;
+    const uint64_t* in_off;   /* n + 1 */
+    uint8_t* out;
+    const uint64_t* out_off;  /* n + 1 */
+    uint64_t* out_len;        /* n */
+    uint32_t* status;         /* n */
+    uint32_t* detail;         /* n */
+    const uint8_t* code_size; /* n or NULL */
+    uint64_t n;
+} slzw_batch;
+
+typedef struct slzw_ctx slzw_ctx;
+
+/* ---- context ------------------------------------------------------------------------------
+ * A context owns the per-device workspace (stream schedule, work queue, staging buffers).
+ * One context per host thread; contexts are independent (the reference's functions are
+ * stateless and re-entrant). */
+int slzw_create(int device, slzw_ctx** ctx);
+void slzw_destroy(slzw_ctx* ctx);
+const char* slzw_last_error(const slzw_ctx* ctx);
+/* kernels launched by this context so far (for benchmark accounting) */
+uint64_t slzw_kernel_launches(const slzw_ctx* ctx);
+uint32_t slzw_version(void);
+
+/* ---- batched entry points (the hot path; new relative to the reference) ----------------- */
+/* Device-resident batch, asynchronous on `cuda_stream` (a cudaStream_t, may be NULL).
+ * Each stream is encoded exactly as VariableEncoder::inner_encode (encoder.rs:273-346) or
+ * FixedEncoder::inner_encode (encoder.rs:618-658) would encode it on its own. */
+int slzw_encode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
+                             void* cuda_stream);
+/* VariableDecoder::inner_decode (decoder.rs:174-290) / FixedDecoder::inner_decode
+ * (decoder.rs:553-642) per stream, same conventions. */
+int slzw_decode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
+                             void* cuda_stream);
+/* Host-resident batch: copies in, runs the device path, copies results back, synchronous.
+ * Buffers from slzw_host_alloc() (pinned) overlap transfers with kernels. */
+int slzw_encode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch);
+int slzw_decode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch);
+
+/* ---- single stream (= batch of one): backs the 16 facade functions ------------------------
+ * Returns SLZW_RC_* (<0) on launch failure, otherwise the stream's slzw_status (>=0). */
+int slzw_encode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
+                uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* detail);
+int slzw_decode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
+                uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* detail);
+
+/* ---- sizing ------------------------------------------------------------------------------ */
+/* Worst-case encoded size of an n-byte stream (what encode_to_vec needs, encoder.rs:268). */
+uint64_t slzw_encode_bound(const slzw_params* params, uint64_t n);
+/* Size-only decode: out_len/status/detail as slzw_decode_batch_device with unlimited
+ * capacity, nothing written (batch->out/out_off may be NULL).  Backs decode_to_vec
+ * (decoder.rs:163-172), which has no caller-supplied capacity. */
+int slzw_decoded_sizes_batch_device(slzw_ctx* ctx, const slzw_params* params,
+                                    const slzw_batch* batch, void* cuda_stream);
+
+/* ---- compaction (scheduler output stage) -------------------------------------------------
+ * dst_off[0..n] = exclusive prefix sum of len[0..n); dst[dst_off[i] .. +len[i]) =
+ * src[src_off[i] .. +len[i]).  Device pointers, asynchronous on `cuda_stream`. */
+int slzw_compact_device(slzw_ctx* ctx, const uint8_t* src, const uint64_t* src_off,
+                        const uint64_t* len, uint64_t n, uint8_t* dst, uint64_t* dst_off,
+                        void* cuda_stream);
+
+/* ---- helpers ----------------------------------------------------------------------------- */
+/* pinned host memory for the *_host entry points */
+void* slzw_host_alloc(size_t bytes);
+void slzw_host_free(void* p);
+/* Formats the reference's Display text for a result (encoder.rs:31-44, decoder.rs:27-42),
+ * e.g. "Code size must be between 2 and 8, was 10." ; returns bytes written (excl. NUL). */
+int slzw_status_message(int is_decoder, uint32_t status, uint32_t detail, uint8_t code_size,
+                        char* buf, size_t buf_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLZW_H */
