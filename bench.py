@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark: batched TIFF-style LZW encode + decode (BASELINE config 3).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--streams S]
+
+One *step* = one pass of the hot path over one batch of synthetic TIFF strips: encode every
+strip, compact the compressed strips into a dense buffer (prefix sum + gather), decode them
+back.  `value` = uncompressed bytes of the batch / step time (so both directions are paid for
+every counted byte), inputs resident in HBM.  `e2e` = the same step through the host-buffer C
+ABI (slzw_{encode,decode}_batch_host) with pinned host memory, copies inside the timed region.
+
+N > 1: one process per GPU (torchrun), every rank owns its own batch of the same shape (weak
+scaling, no data-path collective: streams are independent); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "uncompressed GB/s encode & decode, batched GIF/TIFF streams"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=65536, help="TIFF strips per GPU (config 3: 65,536)")
+    ap.add_argument("--cpu-sample", type=int, default=4096, help="strips in the CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_streams, total_bytes):
+    return {
+        "workload": f"config 3: {n_streams} synthetic TIFF strips per GPU, 8-64 KB, 4 entropy classes "
+                    "(random / photo walk / runs / Zipf text), TIFF-style LZW (MSB-first, early change)",
+        "streams_per_gpu": n_streams,
+        "uncompressed_bytes_per_gpu": int(total_bytes),
+        "step": "encode + compact + decode of the whole batch",
+        "l2": "inputs larger than L2 (no explicit flush)",
+        "sharding": "streams sharded by rank, no collective",
+    }
+
+
+# ---- clocks ----------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---- CPU baseline / reference arm ---------------------------------------------------------------------
+def cpu_pass(buf, off, threads):
+    """One encode + decode pass of the oracle (restatement of salzweg) over a batch.
+    Returns (seconds_encode, seconds_decode)."""
+    from lzw_b200 import workloads as W
+    from oracle import oracle as O
+    slots = W.encode_slots(off)
+    t0 = time.perf_counter()
+    out, out_len, status, _ = O.encode_batch(O.tiff(), buf, off, slots, threads=threads)
+    t1 = time.perf_counter()
+    # dense copy of the encoded strips, untimed (the CPU path writes each strip where it wants)
+    dense_off = np.zeros(off.size, dtype=np.uint64)
+    dense_off[1:] = np.cumsum(out_len)
+    dense = np.empty(int(dense_off[-1]), dtype=np.uint8)
+    for i in range(out_len.size):
+        l = int(out_len[i])
+        dense[int(dense_off[i]):int(dense_off[i]) + l] = out[int(slots[i]):int(slots[i]) + l]
+    t2 = time.perf_counter()
+    O.decode_batch(O.tiff(), dense, dense_off, off, threads=threads)
+    t3 = time.perf_counter()
+    return t1 - t0, t3 - t2
+
+
+def cpu_baseline(buf, off, sample_streams, threads):
+    n = min(sample_streams, off.size - 1)
+    sub_off = off[: n + 1] - off[0]
+    sub = buf[int(off[0]):int(off[n])]
+    te, td = cpu_pass(sub, sub_off, threads)
+    nbytes = int(sub_off[-1])
+    return {
+        "value": nbytes / (te + td) / 1e9,
+        "unit": UNIT,
+        "cores": threads,
+        "kind": "port",
+        "sample": f"first {n} strips of the workload ({nbytes} uncompressed bytes), oracle/slzw_oracle.c "
+                  f"(C restatement of salzweg; the Rust crate cannot be built here), one stream per task "
+                  f"over {threads} host threads",
+        "encode_gbs": nbytes / te / 1e9,
+        "decode_gbs": nbytes / td / 1e9,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from lzw_b200 import workloads as W
+    threads = os.cpu_count() or 1
+    n = min(args.cpu_sample, args.streams)
+    buf, off = W.tiff_strips(n)
+    nbytes = int(off[-1])
+    for _ in range(args.warmup):
+        cpu_pass(buf, off, threads)
+    te = td = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = cpu_pass(buf, off, threads)
+        te += a
+        td += b
+    wall = time.perf_counter() - t0
+    value = nbytes * args.steps / (te + td) / 1e9
+    sample = (f"{n} strips ({nbytes} uncompressed bytes) of config 3 per step, oracle/slzw_oracle.c "
+              f"(C restatement of salzweg; no Rust toolchain to build the crate), {threads} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": workload_config(args, n, nbytes),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "encode_gbs": nbytes * args.steps / te / 1e9,
+                         "decode_gbs": nbytes * args.steps / td / 1e9},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }))
+
+
+# ---- our arm ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import lzw_b200
+    from lzw_b200 import workloads as W
+    from lzw_b200.types import tiff_params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; lzw_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    codec = lzw_b200.Codec(local_rank)
+    params = tiff_params()
+
+    # ---- synthetic batch of this rank (weak scaling: same shape, different seed per rank) ----
+    buf, off = W.tiff_strips(args.streams, seed=W.SEED + 3 + 1000 * rank)
+    n = off.size - 1
+    total = int(off[-1])
+    slots = W.encode_slots(off)
+
+    def i64(a):
+        return torch.from_numpy(a.view(np.int64)).to(dev)
+
+    t_in = torch.from_numpy(buf).to(dev)
+    t_off = i64(off)
+    t_slots = i64(slots)
+    t_enc = torch.empty(int(slots[-1]), dtype=torch.uint8, device=dev)
+    t_enc_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    t_enc_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    t_enc_det = torch.zeros(n, dtype=torch.int32, device=dev)
+    t_dense = torch.empty(int(slots[-1]), dtype=torch.uint8, device=dev)
+    t_dense_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    t_dec = torch.empty(total, dtype=torch.uint8, device=dev)
+    t_dec_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    t_dec_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    t_dec_det = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    def step(ev=None):
+        if ev:
+            ev[0].record(stream)
+        codec.encode_batch_device(params, n, t_in.data_ptr(), t_off.data_ptr(), t_enc.data_ptr(),
+                                  t_slots.data_ptr(), t_enc_len.data_ptr(), t_enc_st.data_ptr(),
+                                  t_enc_det.data_ptr(), stream=sp)
+        if ev:
+            ev[1].record(stream)
+        codec.compact_device(t_enc.data_ptr(), t_slots.data_ptr(), t_enc_len.data_ptr(), n,
+                             t_dense.data_ptr(), t_dense_off.data_ptr(), align=1, stream=sp)
+        if ev:
+            ev[2].record(stream)
+        codec.decode_batch_device(params, n, t_dense.data_ptr(), t_dense_off.data_ptr(), t_dec.data_ptr(),
+                                  t_off.data_ptr(), t_dec_len.data_ptr(), t_dec_st.data_ptr(),
+                                  t_dec_det.data_ptr(), stream=sp)
+        if ev:
+            ev[3].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    launches0 = codec.kernel_launches
+    start = torch.cuda.Event(enable_timing=True)
+    stop = torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record(stream)
+    for k in range(args.steps):
+        step(evs[k])
+    stop.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = codec.kernel_launches - launches0
+    elapsed_ms = start.elapsed_time(stop)
+    enc_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+    cmp_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+    dec_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in evs]))
+
+    # ---- parity properties at full size (outside the timed region) ----
+    enc_st = t_enc_st.cpu().numpy()
+    dec_st = t_dec_st.cpu().numpy()
+    dec_len = t_dec_len.cpu().numpy()
+    comp_total = int(t_dense_off[-1].item())
+    lens = np.diff(off).astype(np.int64)
+    round_trip_bytes_ok = bool(torch.equal(t_dec, t_in))  # SURVEY F1 streams still produce the right bytes
+    parity = {
+        "encode_status_ok": int((enc_st == 0).sum()),
+        "decode_status_ok": int((dec_st == 0).sum()),
+        "decode_len_matches": int((dec_len == lens).sum()),
+        "round_trip_bytes_equal": round_trip_bytes_ok,
+        "self_inconsistent_streams(F1)": int((dec_st != 0).sum()),
+        "compressed_bytes": comp_total,
+    }
+    # oracle check of a sample (bytes, sizes, statuses), rank 0 only
+    if rank == 0:
+        from oracle import oracle as O
+        m = min(512, n)
+        o_out, o_len, o_st, _ = O.encode_batch(O.tiff(), buf[: int(off[m])], off[: m + 1], slots[: m + 1],
+                                               threads=os.cpu_count() or 1)
+        g_len = t_enc_len[:m].cpu().numpy().astype(np.uint64)
+        g_out = t_enc[: int(slots[m])].cpu().numpy()
+        same = bool(np.array_equal(g_len, o_len)) and all(
+            np.array_equal(g_out[int(slots[i]):int(slots[i]) + int(o_len[i])],
+                           o_out[int(slots[i]):int(slots[i]) + int(o_len[i])]) for i in range(m))
+        parity["oracle_sample_streams"] = m
+        parity["oracle_sample_byte_exact"] = same
+
+    # ---- max over ranks ----
+    t = torch.tensor([elapsed_ms, enc_ms, cmp_ms, dec_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, enc_ms, cmp_ms, dec_ms = [float(x) for x in t.tolist()]
+    ms_per_step = elapsed_ms / args.steps
+    value = world * total / (ms_per_step * 1e-3) / 1e9
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory) ----
+    e2e = None
+    if not args.no_e2e:
+        h_in = torch.from_numpy(buf).pin_memory().numpy()
+        h_dense = torch.empty(int(slots[-1]), dtype=torch.uint8).pin_memory().numpy()
+        e2e_steps = max(1, min(args.steps, 3))
+        h2d = d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            dense, doff, st, det = codec.encode_batch_dense(params, h_in, off, out=h_dense)
+            dec, dlen, dst, ddet = codec.decode_batch(params, dense, doff, off)
+            h2d += total + dense.size + 3 * 8 * (n + 1)
+            d2h += dense.size + total + 8 * (n + 1) + 8 * n + 4 * 4 * n
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        e2e = {"value": world * total * e2e_steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
+               "steps": e2e_steps, "round_trip_ok": bool(np.array_equal(dec[:total], buf))}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        comp = parity["compressed_bytes"]
+        kernels = {
+            "encode": {"ms": enc_ms, "algorithmic_bytes": total + comp},
+            "compact": {"ms": cmp_ms, "algorithmic_bytes": 2 * comp},
+            "decode": {"ms": dec_ms, "algorithmic_bytes": total + comp},
+        }
+        for k in kernels.values():
+            k["achieved_gbs"] = k["algorithmic_bytes"] / (k["ms"] * 1e-3) / 1e9
+            k["frac_of_peak"] = k["achieved_gbs"] / peak
+        dom = max(("encode", "decode"), key=lambda k: kernels[k]["ms"])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, n, total),
+            "encode_gbs": world * total / (enc_ms * 1e-3) / 1e9,
+            "decode_gbs": world * total / (dec_ms * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": f"slzw_{dom}_kernel", "achieved": kernels[dom]["achieved_gbs"],
+                         "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": kernels[dom]["frac_of_peak"], "traffic": None,
+                         "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
+                         "launch_ms": kernels[dom]["ms"], "frac_of_nominal_8000": kernels[dom]["achieved_gbs"] / 8000.0},
+            "kernels": kernels,
+            "clocks": clocks, "gpu_launches": int(launches), "parity": parity,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(buf, off, args.cpu_sample, os.cpu_count() or 1)
+        print(json.dumps(line))
+    codec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

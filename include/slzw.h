@@ -33,6 +33,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define SLZW_API __attribute__((visibility("default")))
+#else
+#define SLZW_API
+#endif
+
 #define SLZW_VERSION_MAJOR 0
 #define SLZW_VERSION_MINOR 1
 
@@ -118,58 +124,72 @@ typedef struct slzw_ctx slzw_ctx;
  * A context owns the per-device workspace (stream schedule, work queue, staging buffers).
  * One context per host thread; contexts are independent (the reference's functions are
  * stateless and re-entrant). */
-int slzw_create(int device, slzw_ctx** ctx);
-void slzw_destroy(slzw_ctx* ctx);
-const char* slzw_last_error(const slzw_ctx* ctx);
+SLZW_API int slzw_create(int device, slzw_ctx** ctx);
+SLZW_API void slzw_destroy(slzw_ctx* ctx);
+SLZW_API const char* slzw_last_error(const slzw_ctx* ctx);
 /* kernels launched by this context so far (for benchmark accounting) */
-uint64_t slzw_kernel_launches(const slzw_ctx* ctx);
-uint32_t slzw_version(void);
+SLZW_API uint64_t slzw_kernel_launches(const slzw_ctx* ctx);
+SLZW_API uint32_t slzw_version(void);
 
 /* ---- batched entry points (the hot path; new relative to the reference) ----------------- */
 /* Device-resident batch, asynchronous on `cuda_stream` (a cudaStream_t, may be NULL).
  * Each stream is encoded exactly as VariableEncoder::inner_encode (encoder.rs:273-346) or
  * FixedEncoder::inner_encode (encoder.rs:618-658) would encode it on its own. */
-int slzw_encode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
+SLZW_API int slzw_encode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
                              void* cuda_stream);
 /* VariableDecoder::inner_decode (decoder.rs:174-290) / FixedDecoder::inner_decode
  * (decoder.rs:553-642) per stream, same conventions. */
-int slzw_decode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
+SLZW_API int slzw_decode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
                              void* cuda_stream);
 /* Host-resident batch: copies in, runs the device path, copies results back, synchronous.
  * Buffers from slzw_host_alloc() (pinned) overlap transfers with kernels. */
-int slzw_encode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch);
-int slzw_decode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch);
+SLZW_API int slzw_encode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch);
+SLZW_API int slzw_decode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch);
+
+/* Host-resident batch with DENSE output: stream i's encoded bytes land at
+ * out_dense[out_off[i] .. out_off[i+1]) (out_off has n+1 entries and is written by the call,
+ * out_off[0] = 0, every stream rounded up to `align` bytes).  Worst-case slots live on the
+ * device only; the compaction stage runs before the copy back, so only encoded bytes cross the
+ * bus.  If out_off[n] would exceed out_cap nothing is copied, *needed (if not NULL) receives
+ * the required size and SLZW_RC_NOMEM is returned.  This is what a TIFF/GIF writer wants:
+ * strips back to back plus StripOffsets/StripByteCounts. */
+SLZW_API int slzw_encode_batch_host_dense(slzw_ctx* ctx, const slzw_params* params,
+                                          const uint8_t* in, const uint64_t* in_off, uint64_t n,
+                                          const uint8_t* code_size, uint64_t align,
+                                          uint8_t* out_dense, uint64_t out_cap, uint64_t* out_off,
+                                          uint32_t* status, uint32_t* detail, uint64_t* needed);
 
 /* ---- single stream (= batch of one): backs the 16 facade functions ------------------------
  * Returns SLZW_RC_* (<0) on launch failure, otherwise the stream's slzw_status (>=0). */
-int slzw_encode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
+SLZW_API int slzw_encode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
                 uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* detail);
-int slzw_decode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
+SLZW_API int slzw_decode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
                 uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* detail);
 
 /* ---- sizing ------------------------------------------------------------------------------ */
 /* Worst-case encoded size of an n-byte stream (what encode_to_vec needs, encoder.rs:268). */
-uint64_t slzw_encode_bound(const slzw_params* params, uint64_t n);
+SLZW_API uint64_t slzw_encode_bound(const slzw_params* params, uint64_t n);
 /* Size-only decode: out_len/status/detail as slzw_decode_batch_device with unlimited
  * capacity, nothing written (batch->out/out_off may be NULL).  Backs decode_to_vec
  * (decoder.rs:163-172), which has no caller-supplied capacity. */
-int slzw_decoded_sizes_batch_device(slzw_ctx* ctx, const slzw_params* params,
+SLZW_API int slzw_decoded_sizes_batch_device(slzw_ctx* ctx, const slzw_params* params,
                                     const slzw_batch* batch, void* cuda_stream);
 
 /* ---- compaction (scheduler output stage) -------------------------------------------------
- * dst_off[0..n] = exclusive prefix sum of len[0..n); dst[dst_off[i] .. +len[i]) =
+ * dst_off[0..n] = exclusive prefix sum of len[0..n), each length rounded up to a multiple of
+ * `align` (1 = dense; TIFF strips want 2); dst[dst_off[i] .. +len[i]) =
  * src[src_off[i] .. +len[i]).  Device pointers, asynchronous on `cuda_stream`. */
-int slzw_compact_device(slzw_ctx* ctx, const uint8_t* src, const uint64_t* src_off,
-                        const uint64_t* len, uint64_t n, uint8_t* dst, uint64_t* dst_off,
-                        void* cuda_stream);
+SLZW_API int slzw_compact_device(slzw_ctx* ctx, const uint8_t* src, const uint64_t* src_off,
+                        const uint64_t* len, uint64_t n, uint64_t align, uint8_t* dst,
+                        uint64_t* dst_off, void* cuda_stream);
 
 /* ---- helpers ----------------------------------------------------------------------------- */
 /* pinned host memory for the *_host entry points */
-void* slzw_host_alloc(size_t bytes);
-void slzw_host_free(void* p);
+SLZW_API void* slzw_host_alloc(size_t bytes);
+SLZW_API void slzw_host_free(void* p);
 /* Formats the reference's Display text for a result (encoder.rs:31-44, decoder.rs:27-42),
  * e.g. "Code size must be between 2 and 8, was 10." ; returns bytes written (excl. NUL). */
-int slzw_status_message(int is_decoder, uint32_t status, uint32_t detail, uint8_t code_size,
+SLZW_API int slzw_status_message(int is_decoder, uint32_t status, uint32_t detail, uint8_t code_size,
                         char* buf, size_t buf_len);
 
 #ifdef __cplusplus

@@ -1,0 +1,207 @@
+"""Codec: a libslzw context plus the batched entry points (host and device memory)."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import Batch, Params
+
+
+class SlzwError(RuntimeError):
+    """A launch-level failure (SLZW_RC_*), not a per-stream codec error."""
+
+
+class Codec:
+    """One slzw_ctx bound to one GPU.  Not shared between threads (one per thread)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.lib()
+        h = C.c_void_p()
+        rc = self._lib.slzw_create(device, C.byref(h))
+        if rc != _lib.RC_OK:
+            raise SlzwError(
+                f"slzw_create(device={device}) failed with rc={rc}: "
+                + ("no usable sm_100 CUDA device -- lzw_b200 has no CPU fallback"
+                   if rc == _lib.RC_NO_DEVICE else "CUDA error"))
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.slzw_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- helpers -------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != _lib.RC_OK:
+            raise SlzwError(f"{what} failed (rc={rc}): {self._lib.slzw_last_error(self._h).decode()}")
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.slzw_kernel_launches(self._h))
+
+    def encode_bound(self, params: Params, n: int) -> int:
+        return int(self._lib.slzw_encode_bound(C.byref(params), n))
+
+    # ---- device-resident batches: raw pointers (ints), asynchronous on `stream` ----------
+    def _dev(self, fn, params, n, in_ptr, in_off_ptr, out_ptr, out_off_ptr, out_len_ptr,
+             status_ptr, detail_ptr, code_size_ptr, stream, what):
+        b = Batch(in_ptr, in_off_ptr, out_ptr, out_off_ptr, out_len_ptr, status_ptr, detail_ptr,
+                  code_size_ptr or None, n)
+        self._check(fn(self._h, C.byref(params), C.byref(b), stream or None), what)
+
+    def encode_batch_device(self, params, n, in_ptr, in_off_ptr, out_ptr, out_off_ptr,
+                            out_len_ptr, status_ptr, detail_ptr, code_size_ptr=0, stream=0):
+        self._dev(self._lib.slzw_encode_batch_device, params, n, in_ptr, in_off_ptr, out_ptr,
+                  out_off_ptr, out_len_ptr, status_ptr, detail_ptr, code_size_ptr, stream,
+                  "slzw_encode_batch_device")
+
+    def decode_batch_device(self, params, n, in_ptr, in_off_ptr, out_ptr, out_off_ptr,
+                            out_len_ptr, status_ptr, detail_ptr, code_size_ptr=0, stream=0):
+        self._dev(self._lib.slzw_decode_batch_device, params, n, in_ptr, in_off_ptr, out_ptr,
+                  out_off_ptr, out_len_ptr, status_ptr, detail_ptr, code_size_ptr, stream,
+                  "slzw_decode_batch_device")
+
+    def decoded_sizes_batch_device(self, params, n, in_ptr, in_off_ptr, out_len_ptr, status_ptr,
+                                   detail_ptr, code_size_ptr=0, stream=0):
+        self._dev(self._lib.slzw_decoded_sizes_batch_device, params, n, in_ptr, in_off_ptr, 0, 0,
+                  out_len_ptr, status_ptr, detail_ptr, code_size_ptr, stream,
+                  "slzw_decoded_sizes_batch_device")
+
+    def compact_device(self, src_ptr, src_off_ptr, len_ptr, n, dst_ptr, dst_off_ptr, align=1,
+                       stream=0):
+        self._check(self._lib.slzw_compact_device(self._h, src_ptr, src_off_ptr, len_ptr, n, align,
+                                                  dst_ptr, dst_off_ptr, stream or None),
+                    "slzw_compact_device")
+
+    # ---- host-resident batches: numpy arrays -----------------------------------------------
+    def _host(self, fn, params, in_buf, in_off, out_off, code_size, what):
+        in_buf = np.ascontiguousarray(in_buf, dtype=np.uint8)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+        n = in_off.size - 1
+        out = np.zeros(max(int(out_off[-1]), 1), dtype=np.uint8)
+        out_len = np.zeros(max(n, 1), dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.uint32)
+        detail = np.zeros(max(n, 1), dtype=np.uint32)
+        cs = None if code_size is None else np.ascontiguousarray(code_size, dtype=np.uint8)
+        b = Batch(in_buf.ctypes.data, in_off.ctypes.data, out.ctypes.data, out_off.ctypes.data,
+                  out_len.ctypes.data, status.ctypes.data, detail.ctypes.data,
+                  None if cs is None else cs.ctypes.data, n)
+        self._check(fn(self._h, C.byref(params), C.byref(b)), what)
+        return out, out_len[:n], status[:n], detail[:n]
+
+    def encode_batch(self, params, in_buf, in_off, out_off=None, code_size=None):
+        """Encodes streams in_buf[in_off[i]:in_off[i+1]].  out_off defaults to worst-case slots.
+        Returns (out, out_off, out_len, status, detail)."""
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        if out_off is None:
+            lens = np.diff(in_off)
+            # slzw_encode_bound, vectorised
+            slots = ((lens + 3 + lens // 3838 + 1) * 12 + 7) // 8
+            slots = (slots + 15) // 16 * 16
+            out_off = np.concatenate([[0], np.cumsum(slots)]).astype(np.uint64)
+        out, out_len, status, detail = self._host(self._lib.slzw_encode_batch_host, params, in_buf,
+                                                  in_off, out_off, code_size,
+                                                  "slzw_encode_batch_host")
+        return out, np.asarray(out_off, dtype=np.uint64), out_len, status, detail
+
+    def encode_batch_dense(self, params, in_buf, in_off, code_size=None, align=1, out=None):
+        """Encodes into a dense buffer (strips back to back).  `out` may be a preallocated
+        (pinned) uint8 array; by default it is sized for the worst case.
+        Returns (dense, dense_off, status, detail)."""
+        in_buf = np.ascontiguousarray(in_buf, dtype=np.uint8)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        n = in_off.size - 1
+        if out is None:
+            lens = np.diff(in_off)
+            worst = int((((lens + 3 + lens // 3838 + 1) * 12 + 7) // 8 + align).sum())
+            out = np.empty(max(worst, 1), dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.uint32)
+        detail = np.zeros(max(n, 1), dtype=np.uint32)
+        cs = None if code_size is None else np.ascontiguousarray(code_size, dtype=np.uint8)
+        needed = C.c_uint64(0)
+        rc = self._lib.slzw_encode_batch_host_dense(
+            self._h, C.byref(params), in_buf.ctypes.data, in_off.ctypes.data, n,
+            None if cs is None else cs.ctypes.data, align, out.ctypes.data, out.size,
+            out_off.ctypes.data, status.ctypes.data, detail.ctypes.data, C.byref(needed))
+        self._check(rc, "slzw_encode_batch_host_dense")
+        return out[: int(out_off[-1])], out_off, status[:n], detail[:n]
+
+    def decode_batch(self, params, in_buf, in_off, out_off, code_size=None):
+        """Decodes streams into capacity slots out_off.  Returns (out, out_len, status, detail)."""
+        return self._host(self._lib.slzw_decode_batch_host, params, in_buf, in_off, out_off,
+                          code_size, "slzw_decode_batch_host")
+
+    # ---- single stream ------------------------------------------------------------------------
+    def encode(self, params: Params, data, cap: int | None = None):
+        """Returns (status, detail, bytes produced)."""
+        a = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) \
+            else np.ascontiguousarray(data, dtype=np.uint8)
+        cap = self.encode_bound(params, a.size) if cap is None else cap
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        out_len, detail = C.c_uint64(0), C.c_uint32(0)
+        st = self._lib.slzw_encode(self._h, C.byref(params), a.ctypes.data if a.size else None,
+                                   a.size, out.ctypes.data, cap, C.byref(out_len), C.byref(detail))
+        if st < 0:
+            self._check(st, "slzw_encode")
+        return st, detail.value, out[: out_len.value].tobytes()
+
+    def decoded_size(self, params: Params, data):
+        a = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) \
+            else np.ascontiguousarray(data, dtype=np.uint8)
+        out_len, detail = C.c_uint64(0), C.c_uint32(0)
+        st = self._lib.slzw_decode(self._h, C.byref(params), a.ctypes.data if a.size else None,
+                                   a.size, None, 0, C.byref(out_len), C.byref(detail))
+        if st < 0:
+            self._check(st, "slzw_decode(size)")
+        return st, detail.value, int(out_len.value)
+
+    def decode(self, params: Params, data, cap: int | None = None):
+        """Returns (status, detail, bytes produced).  cap=None sizes the output first, which is
+        what decode_to_vec's growing Vec amounts to (decoder.rs:163-172)."""
+        a = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) \
+            else np.ascontiguousarray(data, dtype=np.uint8)
+        if cap is None:
+            _, _, cap = self.decoded_size(params, a)
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        out_len, detail = C.c_uint64(0), C.c_uint32(0)
+        st = self._lib.slzw_decode(self._h, C.byref(params), a.ctypes.data if a.size else None,
+                                   a.size, out.ctypes.data, cap, C.byref(out_len), C.byref(detail))
+        if st < 0:
+            self._check(st, "slzw_decode")
+        return st, detail.value, out[: out_len.value].tobytes()
+
+    def status_message(self, is_decoder: bool, status: int, detail: int, code_size: int = 0) -> str:
+        return status_message(is_decoder, status, detail, code_size)
+
+
+def status_message(is_decoder: bool, status: int, detail: int, code_size: int = 0) -> str:
+    """The reference's Display text for a result (encoder.rs:31-44, decoder.rs:27-42)."""
+    buf = C.create_string_buffer(160)
+    _lib.lib().slzw_status_message(int(is_decoder), status, detail, code_size & 0xFF, buf, len(buf))
+    return buf.value.decode()
+
+
+_default = threading.local()
+
+
+def default_codec(device: int = 0) -> Codec:
+    """A per-thread Codec on `device`, created on first use (the reference's functions are
+    stateless, so the facade needs an implicit context)."""
+    key = f"codec{device}"
+    c = getattr(_default, key, None)
+    if c is None:
+        c = Codec(device)
+        setattr(_default, key, c)
+    return c

@@ -1,0 +1,548 @@
+// slzw_api.cu -- the C ABI of include/slzw.h: contexts, scheduling, launches, host staging.
+//
+// There is no CPU code path for the codec in this file: every data-moving entry point ends in
+// the sm_100a kernels of encode_kernels.cu / decode_kernels.cu / sched_kernels.cu and returns
+// SLZW_RC_NO_DEVICE / SLZW_RC_CUDA when that is impossible.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "slzw_device.cuh"
+
+namespace slzw {
+// encode_kernels.cu
+size_t encode_smem_bytes();
+int encode_warps_per_cta();
+cudaError_t encode_configure();
+cudaError_t encode_launch(const DevBatch& a, int grid, cudaStream_t stream);
+// decode_kernels.cu
+size_t decode_exact_smem_bytes();
+int decode_exact_warps_per_cta();
+cudaError_t decode_exact_configure();
+cudaError_t decode_exact_launch(const DevBatch& a, int grid, cudaStream_t stream);
+// sched_kernels.cu
+int sched_size_classes();
+cudaError_t sched_build_order(const uint64_t* off, uint64_t n, uint32_t* hist, uint32_t* order,
+                              int num_sms, cudaStream_t stream);
+cudaError_t compact_launch(const uint8_t* src, const uint64_t* src_off, const uint64_t* len,
+                           uint64_t n, uint64_t align, uint8_t* dst, uint64_t* dst_off, int num_sms,
+                           cudaStream_t stream);
+}  // namespace slzw
+
+using namespace slzw;
+
+namespace {
+
+// A grow-only device allocation.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Scheduler scratch for one in-flight batch.  Reuse on another CUDA stream waits for `done`.
+struct Workspace {
+    DevBuf queue;  // one unsigned long long
+    DevBuf hist;   // size classes
+    DevBuf order;  // n u32
+    cudaEvent_t done = nullptr;
+    bool used = false;
+};
+
+constexpr int kWorkspaces = 4;
+
+}  // namespace
+
+struct slzw_ctx {
+    int device = 0;
+    int num_sms = 0;
+    Workspace ws[kWorkspaces];
+    int ws_next = 0;
+    // host-path staging (device side)
+    DevBuf d_in, d_out, d_in_off, d_out_off, d_out_len, d_status, d_detail, d_cs, d_dense, d_dense_off;
+    cudaStream_t stream = nullptr;  // host-path stream
+    uint64_t launches = 0;
+    char err[256] = {0};
+    std::mutex mu;
+};
+
+namespace {
+
+int fail_cuda(slzw_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) snprintf(ctx->err, sizeof ctx->err, "%s: %s", what, cudaGetErrorString(e));
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? SLZW_RC_NO_DEVICE
+                                                                         : SLZW_RC_CUDA;
+}
+
+#define CK(call, what)                                          \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return fail_cuda(ctx, e__, what); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+bool params_ok(const slzw_params* p) {
+    return p && (p->flavour == SLZW_FLAVOUR_VARIABLE || p->flavour == SLZW_FLAVOUR_FIXED);
+}
+
+// Picks a workspace, makes `stream` wait for its previous user, builds the processing order.
+int prepare(slzw_ctx* ctx, const uint64_t* d_in_off, uint64_t n, cudaStream_t stream,
+            Workspace** out_ws) {
+    Workspace& w = ctx->ws[ctx->ws_next];
+    ctx->ws_next = (ctx->ws_next + 1) % kWorkspaces;
+    if (!w.done) CK(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming), "cudaEventCreate");
+    if (w.used) CK(cudaStreamWaitEvent(stream, w.done, 0), "cudaStreamWaitEvent");
+    CK(w.queue.reserve(sizeof(unsigned long long)), "cudaMalloc(queue)");
+    CK(w.hist.reserve(sizeof(uint32_t) * sched_size_classes()), "cudaMalloc(hist)");
+    CK(w.order.reserve(sizeof(uint32_t) * n), "cudaMalloc(order)");
+    CK(cudaMemsetAsync(w.queue.p, 0, sizeof(unsigned long long), stream), "cudaMemsetAsync(queue)");
+    CK(sched_build_order(d_in_off, n, (uint32_t*)w.hist.p, (uint32_t*)w.order.p, ctx->num_sms,
+                         stream),
+       "scheduler launch");
+    ctx->launches += 3;
+    *out_ws = &w;
+    return SLZW_RC_OK;
+}
+
+int finish(slzw_ctx* ctx, Workspace* w, cudaStream_t stream) {
+    CK(cudaEventRecord(w->done, stream), "cudaEventRecord");
+    w->used = true;
+    return SLZW_RC_OK;
+}
+
+DevBatch make_dev_batch(const slzw_params* params, const slzw_batch* b, const Workspace* w) {
+    DevBatch a;
+    a.in = b->in;
+    a.in_off = b->in_off;
+    a.out = b->out;
+    a.out_off = b->out_off;
+    a.out_len = b->out_len;
+    a.status = b->status;
+    a.detail = b->detail;
+    a.code_size = b->code_size;
+    a.n = b->n;
+    a.order = (const uint32_t*)w->order.p;
+    a.queue = (unsigned long long*)w->queue.p;
+    a.p = *params;
+    return a;
+}
+
+int grid_for(const slzw_ctx* ctx, uint64_t n, int warps_per_cta) {
+    const uint64_t ctas = (n + warps_per_cta - 1) / warps_per_cta;
+    return (int)(ctas < (uint64_t)ctx->num_sms ? ctas : (uint64_t)ctx->num_sms);
+}
+
+enum class Op { Encode, Decode, DecodedSizes };
+
+int run_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, cudaStream_t stream,
+               Op op) {
+    if (!ctx) return SLZW_RC_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!params_ok(params) || !b) {
+        snprintf(ctx->err, sizeof ctx->err, "invalid params or batch");
+        return SLZW_RC_INVALID;
+    }
+    if (b->n == 0) return SLZW_RC_OK;
+    const bool needs_out = op != Op::DecodedSizes;
+    if (!b->in_off || !b->out_len || !b->status || !b->detail || b->n > 0xFFFFFFFFull ||
+        (needs_out && (!b->out || !b->out_off))) {
+        snprintf(ctx->err, sizeof ctx->err, "invalid batch (null pointer or n >= 2^32)");
+        return SLZW_RC_INVALID;
+    }
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
+    Workspace* w = nullptr;
+    int rc = prepare(ctx, b->in_off, b->n, stream, &w);
+    if (rc != SLZW_RC_OK) return rc;
+    DevBatch a = make_dev_batch(params, b, w);
+    if (op == Op::DecodedSizes) {
+        a.out = nullptr;
+        a.out_off = nullptr;
+    }
+    if (op == Op::Encode) {
+        CK(encode_launch(a, grid_for(ctx, b->n, encode_warps_per_cta()), stream), "encode launch");
+    } else {
+        CK(decode_exact_launch(a, grid_for(ctx, b->n, decode_exact_warps_per_cta()), stream),
+           "decode launch");
+    }
+    ctx->launches += 1;
+    return finish(ctx, w, stream);
+}
+
+// Host path: stage the whole batch on the device, run, copy back.
+int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op op) {
+    if (!ctx) return SLZW_RC_INVALID;
+    if (!params_ok(params) || !b) {
+        snprintf(ctx->err, sizeof ctx->err, "invalid params or batch");
+        return SLZW_RC_INVALID;
+    }
+    const uint64_t n = b->n;
+    if (n == 0) return SLZW_RC_OK;
+    const bool needs_out = op != Op::DecodedSizes;
+    if (!b->in_off || !b->out_len || !b->status || !b->detail ||
+        (needs_out && (!b->out || !b->out_off)) || (b->in_off[n] > 0 && !b->in)) {
+        snprintf(ctx->err, sizeof ctx->err, "invalid batch (null pointer)");
+        return SLZW_RC_INVALID;
+    }
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t s = ctx->stream;
+    const uint64_t in_lo = b->in_off[0], in_hi = b->in_off[n];
+    const uint64_t out_lo = needs_out ? b->out_off[0] : 0, out_hi = needs_out ? b->out_off[n] : 0;
+    slzw_batch d = {};
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        CK(ctx->d_in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
+        CK(ctx->d_out.reserve(out_hi - out_lo + 16), "cudaMalloc(out)");
+        CK(ctx->d_in_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(in_off)");
+        CK(ctx->d_out_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(out_off)");
+        CK(ctx->d_out_len.reserve(sizeof(uint64_t) * n), "cudaMalloc(out_len)");
+        CK(ctx->d_status.reserve(sizeof(uint32_t) * n), "cudaMalloc(status)");
+        CK(ctx->d_detail.reserve(sizeof(uint32_t) * n), "cudaMalloc(detail)");
+        if (b->code_size) CK(ctx->d_cs.reserve(n), "cudaMalloc(code_size)");
+    }
+    // Offsets stay absolute: the device copies of in/out are biased by -lo instead.
+    if (in_hi > in_lo)
+        CK(cudaMemcpyAsync(ctx->d_in.p, b->in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s),
+           "H2D in");
+    CK(cudaMemcpyAsync(ctx->d_in_off.p, b->in_off, sizeof(uint64_t) * (n + 1),
+                       cudaMemcpyHostToDevice, s), "H2D in_off");
+    if (needs_out)
+        CK(cudaMemcpyAsync(ctx->d_out_off.p, b->out_off, sizeof(uint64_t) * (n + 1),
+                           cudaMemcpyHostToDevice, s), "H2D out_off");
+    if (b->code_size)
+        CK(cudaMemcpyAsync(ctx->d_cs.p, b->code_size, n, cudaMemcpyHostToDevice, s), "H2D code_size");
+    d.in = (const uint8_t*)ctx->d_in.p - in_lo;
+    d.in_off = (const uint64_t*)ctx->d_in_off.p;
+    d.out = needs_out ? (uint8_t*)ctx->d_out.p - out_lo : nullptr;
+    d.out_off = needs_out ? (const uint64_t*)ctx->d_out_off.p : nullptr;
+    d.out_len = (uint64_t*)ctx->d_out_len.p;
+    d.status = (uint32_t*)ctx->d_status.p;
+    d.detail = (uint32_t*)ctx->d_detail.p;
+    d.code_size = b->code_size ? (const uint8_t*)ctx->d_cs.p : nullptr;
+    d.n = n;
+    int rc = run_device(ctx, params, &d, s, op);
+    if (rc != SLZW_RC_OK) return rc;
+    if (needs_out && out_hi > out_lo)
+        CK(cudaMemcpyAsync(b->out + out_lo, ctx->d_out.p, out_hi - out_lo, cudaMemcpyDeviceToHost, s),
+           "D2H out");
+    CK(cudaMemcpyAsync(b->out_len, ctx->d_out_len.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, s),
+       "D2H out_len");
+    CK(cudaMemcpyAsync(b->status, ctx->d_status.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s),
+       "D2H status");
+    CK(cudaMemcpyAsync(b->detail, ctx->d_detail.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s),
+       "D2H detail");
+    CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    return SLZW_RC_OK;
+}
+
+// Host path with dense output: worst-case slots stay on the device, compaction before D2H.
+int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
+                          const uint64_t* in_off, uint64_t n, const uint8_t* code_size,
+                          uint64_t align, uint8_t* out_dense, uint64_t out_cap, uint64_t* out_off,
+                          uint32_t* status, uint32_t* detail, uint64_t* needed) {
+    if (!ctx) return SLZW_RC_INVALID;
+    if (!params_ok(params) || !in_off || !out_off || !status || !detail || (n && !out_dense) ||
+        (n && in_off[n] > in_off[0] && !in)) {
+        snprintf(ctx->err, sizeof ctx->err, "invalid arguments");
+        return SLZW_RC_INVALID;
+    }
+    out_off[0] = 0;
+    if (needed) *needed = 0;
+    if (n == 0) return SLZW_RC_OK;
+    if (align == 0) align = 1;
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t s = ctx->stream;
+    const uint64_t in_lo = in_off[0], in_hi = in_off[n];
+    // worst-case slots, 16-byte aligned so that the packer's word stores are aligned
+    std::vector<uint64_t> slots(n + 1);
+    slots[0] = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t b = slzw_encode_bound(params, in_off[i + 1] - in_off[i]);
+        slots[i + 1] = slots[i] + ((b + 15) & ~15ull);
+    }
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        CK(ctx->d_in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
+        CK(ctx->d_out.reserve(slots[n] + 16), "cudaMalloc(slots)");
+        CK(ctx->d_dense.reserve(slots[n] + align * n + 16), "cudaMalloc(dense)");
+        CK(ctx->d_in_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(in_off)");
+        CK(ctx->d_out_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(out_off)");
+        CK(ctx->d_dense_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(dense_off)");
+        CK(ctx->d_out_len.reserve(sizeof(uint64_t) * n), "cudaMalloc(out_len)");
+        CK(ctx->d_status.reserve(sizeof(uint32_t) * n), "cudaMalloc(status)");
+        CK(ctx->d_detail.reserve(sizeof(uint32_t) * n), "cudaMalloc(detail)");
+        if (code_size) CK(ctx->d_cs.reserve(n), "cudaMalloc(code_size)");
+    }
+    if (in_hi > in_lo)
+        CK(cudaMemcpyAsync(ctx->d_in.p, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
+    CK(cudaMemcpyAsync(ctx->d_in_off.p, in_off, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s),
+       "H2D in_off");
+    CK(cudaMemcpyAsync(ctx->d_out_off.p, slots.data(), sizeof(uint64_t) * (n + 1),
+                       cudaMemcpyHostToDevice, s), "H2D slots");
+    if (code_size) CK(cudaMemcpyAsync(ctx->d_cs.p, code_size, n, cudaMemcpyHostToDevice, s), "H2D code_size");
+    slzw_batch d = {};
+    d.in = (const uint8_t*)ctx->d_in.p - in_lo;
+    d.in_off = (const uint64_t*)ctx->d_in_off.p;
+    d.out = (uint8_t*)ctx->d_out.p;
+    d.out_off = (const uint64_t*)ctx->d_out_off.p;
+    d.out_len = (uint64_t*)ctx->d_out_len.p;
+    d.status = (uint32_t*)ctx->d_status.p;
+    d.detail = (uint32_t*)ctx->d_detail.p;
+    d.code_size = code_size ? (const uint8_t*)ctx->d_cs.p : nullptr;
+    d.n = n;
+    int rc = run_device(ctx, params, &d, s, Op::Encode);
+    if (rc != SLZW_RC_OK) return rc;
+    CK(compact_launch((const uint8_t*)ctx->d_out.p, (const uint64_t*)ctx->d_out_off.p,
+                      (const uint64_t*)ctx->d_out_len.p, n, align, (uint8_t*)ctx->d_dense.p,
+                      (uint64_t*)ctx->d_dense_off.p, ctx->num_sms, s), "compaction launch");
+    ctx->launches += 2;
+    CK(cudaMemcpyAsync(out_off, ctx->d_dense_off.p, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s),
+       "D2H dense_off");
+    CK(cudaMemcpyAsync(status, ctx->d_status.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s), "D2H status");
+    CK(cudaMemcpyAsync(detail, ctx->d_detail.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s), "D2H detail");
+    CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    const uint64_t total = out_off[n];
+    if (needed) *needed = total;
+    if (total > out_cap) {
+        snprintf(ctx->err, sizeof ctx->err, "dense output needs %llu bytes, capacity is %llu",
+                 (unsigned long long)total, (unsigned long long)out_cap);
+        return SLZW_RC_NOMEM;
+    }
+    if (total) {
+        CK(cudaMemcpyAsync(out_dense, ctx->d_dense.p, total, cudaMemcpyDeviceToHost, s), "D2H dense");
+        CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    }
+    return SLZW_RC_OK;
+}
+
+int run_single(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
+               uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* detail, Op op) {
+    uint64_t in_off[2] = {0, n};
+    uint64_t out_off[2] = {0, cap};
+    uint64_t len = 0;
+    uint32_t st = 0, det = 0;
+    uint8_t dummy = 0;
+    slzw_batch b = {};
+    b.in = in ? in : &dummy;
+    b.in_off = in_off;
+    b.out = out ? out : &dummy;
+    b.out_off = out_off;
+    b.out_len = &len;
+    b.status = &st;
+    b.detail = &det;
+    b.n = 1;
+    if (!out) out_off[1] = 0;
+    int rc = run_host(ctx, params, &b, op);
+    if (rc != SLZW_RC_OK) return rc;
+    if (out_len) *out_len = len;
+    if (detail) *detail = det;
+    return (int)st;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t slzw_version(void) { return (SLZW_VERSION_MAJOR << 16) | SLZW_VERSION_MINOR; }
+
+int slzw_create(int device, slzw_ctx** out) {
+    if (!out) return SLZW_RC_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return SLZW_RC_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SLZW_RC_NO_DEVICE;
+    if (prop.major != 10) return SLZW_RC_NO_DEVICE;  // kernels are built for sm_100a only
+    slzw_ctx* ctx = new (std::nothrow) slzw_ctx;
+    if (!ctx) return SLZW_RC_NOMEM;
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    DeviceGuard guard(device);
+    if (!guard.ok || encode_configure() != cudaSuccess || decode_exact_configure() != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SLZW_RC_CUDA;
+    }
+    *out = ctx;
+    return SLZW_RC_OK;
+}
+
+void slzw_destroy(slzw_ctx* ctx) {
+    if (!ctx) return;
+    {
+        DeviceGuard guard(ctx->device);
+        cudaDeviceSynchronize();
+        for (auto& w : ctx->ws) {
+            w.queue.release();
+            w.hist.release();
+            w.order.release();
+            if (w.done) cudaEventDestroy(w.done);
+        }
+        for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_in_off, &ctx->d_out_off, &ctx->d_out_len,
+                          &ctx->d_status, &ctx->d_detail, &ctx->d_cs, &ctx->d_dense, &ctx->d_dense_off})
+            b->release();
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+const char* slzw_last_error(const slzw_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+uint64_t slzw_kernel_launches(const slzw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int slzw_encode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
+                             void* cuda_stream) {
+    return run_device(ctx, params, batch, (cudaStream_t)cuda_stream, Op::Encode);
+}
+
+int slzw_decode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
+                             void* cuda_stream) {
+    return run_device(ctx, params, batch, (cudaStream_t)cuda_stream, Op::Decode);
+}
+
+int slzw_decoded_sizes_batch_device(slzw_ctx* ctx, const slzw_params* params,
+                                    const slzw_batch* batch, void* cuda_stream) {
+    return run_device(ctx, params, batch, (cudaStream_t)cuda_stream, Op::DecodedSizes);
+}
+
+int slzw_encode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch) {
+    return run_host(ctx, params, batch, Op::Encode);
+}
+
+int slzw_decode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch) {
+    return run_host(ctx, params, batch, Op::Decode);
+}
+
+int slzw_encode_batch_host_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
+                                 const uint64_t* in_off, uint64_t n, const uint8_t* code_size,
+                                 uint64_t align, uint8_t* out_dense, uint64_t out_cap,
+                                 uint64_t* out_off, uint32_t* status, uint32_t* detail,
+                                 uint64_t* needed) {
+    return run_host_encode_dense(ctx, params, in, in_off, n, code_size, align, out_dense, out_cap,
+                                 out_off, status, detail, needed);
+}
+
+int slzw_encode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
+                uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* detail) {
+    return run_single(ctx, params, in, n, out, cap, out_len, detail, Op::Encode);
+}
+
+int slzw_decode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
+                uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* detail) {
+    return run_single(ctx, params, in, n, out, cap, out_len, detail,
+                      out ? Op::Decode : Op::DecodedSizes);
+}
+
+uint64_t slzw_encode_bound(const slzw_params* params, uint64_t n) {
+    (void)params;
+    // One code per input byte at most (encoder.rs:322-324), plus the leading clear, one clear
+    // per dictionary reset (a reset needs >= 3838 emitted codes: 4096 - 258), the final prefix
+    // and EOI; every code <= 12 bits; fill() pads to a byte.
+    const uint64_t codes = n + 3 + n / 3838 + 1;
+    return (codes * 12 + 7) / 8;
+}
+
+int slzw_compact_device(slzw_ctx* ctx, const uint8_t* src, const uint64_t* src_off,
+                        const uint64_t* len, uint64_t n, uint64_t align, uint8_t* dst,
+                        uint64_t* dst_off, void* cuda_stream) {
+    if (!ctx) return SLZW_RC_INVALID;
+    if (!dst_off || (n && (!src || !src_off || !len || !dst))) {
+        snprintf(ctx->err, sizeof ctx->err, "invalid compaction arguments");
+        return SLZW_RC_INVALID;
+    }
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
+    CK(compact_launch(src, src_off, len, n, align, dst, dst_off, ctx->num_sms,
+                      (cudaStream_t)cuda_stream), "compaction launch");
+    ctx->launches += 2;
+    return SLZW_RC_OK;
+}
+
+void* slzw_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void slzw_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int slzw_status_message(int is_decoder, uint32_t status, uint32_t detail, uint8_t code_size,
+                        char* buf, size_t buf_len) {
+    if (!buf || buf_len == 0) return 0;
+    int w = 0;
+    switch (status) {
+        case SLZW_OK:
+            w = snprintf(buf, buf_len, "ok");
+            break;
+        case SLZW_ERR_CODE_SIZE:  // encoder.rs:35-37 (trailing period) vs decoder.rs:31-33
+            w = snprintf(buf, buf_len, is_decoder ? "Code size must be between 2 and 8, was %u"
+                                                  : "Code size must be between 2 and 8, was %u.",
+                         detail);
+            break;
+        case SLZW_ERR_UNEXPECTED_CODE:  // encoder.rs:38-41, decoder.rs:34-36
+            if (is_decoder)
+                w = snprintf(buf, buf_len, "Unexpected code while decompressing: %u", detail);
+            else
+                w = snprintf(buf, buf_len,
+                             "Unexpected code %u. For code size %u, data should be < %u.", detail,
+                             (unsigned)code_size, 1u << code_size);
+            break;
+        case SLZW_ERR_MISSING_CLEAR_CODE:  // decoder.rs:37-39 (sic)
+            w = snprintf(buf, buf_len, "Dictionnary growing past 4096, expected CLEAR_CODE missing");
+            break;
+        case SLZW_ERR_IO_UNEXPECTED_EOF:  // std::io::ErrorKind::UnexpectedEof via read_exact
+            w = snprintf(buf, buf_len, "failed to fill whole buffer");
+            break;
+        case SLZW_ERR_IO_WRITE_ZERO:  // std::io::ErrorKind::WriteZero via write_all
+            w = snprintf(buf, buf_len, "failed to write whole buffer");
+            break;
+        case SLZW_ERR_REFERENCE_PANIC:
+            w = snprintf(buf, buf_len, "the reference implementation panics on this input");
+            break;
+        default:
+            w = snprintf(buf, buf_len, "unknown status %u", status);
+    }
+    if (w < 0) return 0;
+    return (size_t)w < buf_len ? w : (int)buf_len - 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,55 @@
+// slzw_device.cuh -- definitions shared by the sm_100a kernels and the C-ABI host layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slzw.h"
+
+namespace slzw {
+
+constexpr int kWarpSize = 32;
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+// Device view of slzw_batch plus the schedule produced by the stream scheduler.
+struct DevBatch {
+    const uint8_t* in;
+    const uint64_t* in_off;
+    uint8_t* out;             // nullptr => size-only pass (nothing is written)
+    const uint64_t* out_off;  // may be nullptr when out == nullptr
+    uint64_t* out_len;
+    uint32_t* status;
+    uint32_t* detail;
+    const uint8_t* code_size;  // per-stream override or nullptr
+    uint64_t n;
+    const uint32_t* order;          // stream ids in processing order (largest first) or nullptr
+    unsigned long long* queue;      // work-queue head, zeroed before the launch
+    slzw_params p;
+};
+
+// ---- stream staging -------------------------------------------------------------------------
+// Copies src[0..len) into a shared-memory tile so that byte j lands at tile[skew + j], where
+// skew = (address of src) & 15.  Interior 16-byte chunks use aligned vector loads; the ragged
+// head and tail use byte loads, so nothing outside [src, src+len) is ever touched.
+// Returns skew.  `tile` must be 16-byte aligned and hold len + 16 bytes.
+__device__ __forceinline__ uint32_t stage_tile(const uint8_t* __restrict__ src, uint32_t len,
+                                               uint8_t* tile, int lane) {
+    const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint8_t* base = src - skew;  // 16-byte aligned
+    const uint32_t span = skew + len;  // bytes of the aligned window that matter
+    const uint32_t nchunks = (span + 15u) >> 4;
+    for (uint32_t c = lane; c < nchunks; c += kWarpSize) {
+        const uint32_t lo = c << 4;
+        if (lo >= skew && lo + 16u <= span) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + lo));
+            *reinterpret_cast<uint4*>(tile + lo) = v;
+        } else {
+            for (uint32_t b = 0; b < 16u; b++) {
+                const uint32_t o = lo + b;
+                if (o >= skew && o < span) tile[o] = __ldg(base + o);
+            }
+        }
+    }
+    return skew;
+}
+
+}  // namespace slzw

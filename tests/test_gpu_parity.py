@@ -1,0 +1,396 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle, bit-exact.
+
+Every test here calls libslzw.so (via lzw_b200) on cuda:0 and compares out_len / status /
+detail / bytes with the oracle on the same seeded inputs.
+"""
+import hashlib
+import io
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import cases as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def codec():
+    import lzw_b200
+    c = lzw_b200.Codec(0)
+    yield c
+    c.close()
+
+
+def gp(p):
+    """oracle Params -> library Params (same field layout)."""
+    from lzw_b200 import _lib
+    return _lib.Params(p.flavour, p.code_size, p.big_endian, p.tiff_early_change)
+
+
+# ---- reference known-answer vectors, now through the GPU ---------------------------------------
+def test_kat_encode(codec, lorem, lorem_encoded):
+    assert codec.encode(gp(O.variable(2, False, False)), T.D40)[2] == bytes(
+        [0x8C, 0x2D, 0x99, 0x87, 0x2A, 0x1C, 0xDC, 0x33, 0xA0, 0x02, 0x55, 0x00])   # encoder.rs:666-686
+    assert codec.encode(gp(O.gif(2)), bytes([0, 0, 1, 3])) == (0, 0, bytes([0x04, 0x32, 0x05]))
+    assert codec.encode(gp(O.tiff()), bytes([0, 0, 1, 3])) == (0, 0, bytes([0x80, 0, 0, 0, 0x10, 0x1C, 0x04]))
+    assert codec.encode(gp(O.fixed()), bytes([0, 0, 1, 3])) == (0, 0, bytes([0, 0, 0, 1, 0x30, 0]))
+    st, _, out = codec.encode(gp(O.gif(7)), lorem)                                    # encoder.rs:740-755
+    assert st == 0 and out == lorem_encoded
+    assert codec.encode(gp(O.variable(10, False, False)), bytes([0]))[:2] == (O.ERR_CODE_SIZE, 10)
+    assert codec.encode(gp(O.variable(2, True, False)), bytes([0, 1, 8, 3]))[:2] == (O.ERR_UNEXPECTED_CODE, 8)
+
+
+def test_kat_decode(codec, lorem, lorem_encoded):
+    assert codec.decode(gp(O.gif(7)), lorem_encoded) == (0, 0, lorem)                # decoder.rs:703-718
+    assert codec.decode(gp(O.variable(2, False, False)), bytes(
+        [0x8C, 0x2D, 0x99, 0x87, 0x2A, 0x1C, 0xDC, 0x33, 0xA0, 0x02, 0x55, 0x00])) == (0, 0, T.D40)
+    assert codec.decode(gp(O.variable(10, False, False)), bytes([0]))[:2] == (O.ERR_CODE_SIZE, 10)
+    st, detail, _ = codec.decode(gp(O.tiff()), T.BAD_TIFF)                           # decoder.rs:759-769
+    assert (st, detail) == (O.ERR_UNEXPECTED_CODE, 258)
+
+
+def test_facade_matches_reference_api(lorem, lorem_encoded):
+    """The reference-shaped facade (same names / arguments / error text)."""
+    from lzw_b200 import CodeSizeStrategy, Endianness
+    from lzw_b200.decoder import (DecodingError, FixedDecoder, GifStyleDecoder, TiffStyleDecoder,
+                                  VariableDecoder)
+    from lzw_b200.encoder import (EncodingError, FixedEncoder, GifStyleEncoder, TiffStyleEncoder,
+                                  VariableEncoder)
+    data = bytes([0, 0, 1, 3])
+    assert GifStyleEncoder.encode_to_vec(data, 2) == bytes([0x04, 0x32, 0x05])
+    assert TiffStyleEncoder.encode_to_vec(data) == bytes([0x80, 0, 0, 0, 0x10, 0x1C, 0x04])
+    assert FixedEncoder.encode_to_vec(data, Endianness.LittleEndian) == bytes([0, 0, 0, 1, 0x30, 0])
+    assert VariableEncoder.encode_to_vec(data, 2, Endianness.LittleEndian, CodeSizeStrategy.Default) == bytes([0x04, 0x32, 0x05])
+    assert GifStyleDecoder.decode_to_vec(bytes([0x04, 0x32, 0x05]), 2) == data
+    assert TiffStyleDecoder.decode_to_vec(bytes([0x80, 0, 0, 0, 0x10, 0x1C, 0x04])) == data
+    assert FixedDecoder.decode_to_vec(bytes([0, 0, 0, 1, 0x30, 0]), Endianness.LittleEndian) == data
+    sink = io.BytesIO()
+    VariableEncoder.encode(io.BytesIO(lorem), sink, 7, Endianness.LittleEndian, CodeSizeStrategy.Default)
+    assert sink.getvalue() == lorem_encoded                                           # examples/usage.rs
+    out = bytearray()
+    VariableDecoder.decode(lorem_encoded, out, 7, Endianness.LittleEndian, CodeSizeStrategy.Default)
+    assert bytes(out) == lorem
+    with pytest.raises(EncodingError) as e:                                           # encoder.rs:758-774
+        VariableEncoder.encode(bytes([0]), bytearray(), 10, Endianness.LittleEndian, CodeSizeStrategy.Default)
+    assert str(e.value) == "Code size must be between 2 and 8, was 10."
+    with pytest.raises(EncodingError) as e:                                           # encoder.rs:777-795
+        VariableEncoder.encode_to_vec(bytes([0, 1, 8, 3]), 2, Endianness.BigEndian, CodeSizeStrategy.Default)
+    assert str(e.value) == "Unexpected code 8. For code size 2, data should be < 4."
+    with pytest.raises(DecodingError) as e:                                           # decoder.rs:721-737
+        VariableDecoder.decode(bytes([0]), bytearray(), 10, Endianness.LittleEndian, CodeSizeStrategy.Default)
+    assert str(e.value) == "Code size must be between 2 and 8, was 10"
+    with pytest.raises(DecodingError) as e:                                           # decoder.rs:759-769
+        TiffStyleDecoder.decode_to_vec(T.BAD_TIFF)
+    assert str(e.value) == "Unexpected code while decompressing: 258"
+
+
+# ---- config 1: lorem through every flavour -------------------------------------------------------
+@pytest.mark.parametrize("p", T.all_params(), ids=T.pname)
+def test_lorem_every_flavour(codec, lorem, p):
+    data = bytes(b & T.max_symbol(p) for b in lorem) if T.max_symbol(p) < 127 else lorem
+    want = O.encode(p, data)
+    got = codec.encode(gp(p), data)
+    assert got == want
+    assert codec.decode(gp(p), got[2]) == O.decode(p, want[2])
+
+
+# ---- config 2: sunflower strips, TIFF ----------------------------------------------------------------
+def test_sunflower_strips_tiff(codec):
+    from lzw_b200 import workloads as W
+    px, off = W.sunflower_strips()
+    out, out_off, out_len, status, detail = codec.encode_batch(gp(O.tiff()), px, off)
+    assert (status == 0).all()
+    assert out_len.tolist() == [5712, 6461, 5872, 5996, 7242, 7983, 8079, 8407, 8190, 7944, 6900, 3618, 1982, 561]
+    dense, doff = T.pack_dense(out, out_off, out_len)
+    assert hashlib.sha256(dense.tobytes()).hexdigest().startswith("2a13fbbe2522f966")
+    o_out, o_len, o_st, _ = O.encode_batch(O.tiff(), px, off, out_off)
+    assert np.array_equal(o_len, out_len) and T.slots_equal(out, o_out, out_off, out_len) < 0
+    dec, dlen, dst, _ = codec.decode_batch(gp(O.tiff()), dense, doff, off)
+    assert (dst == 0).all() and np.array_equal(dlen, np.diff(off)) and np.array_equal(dec[:px.size], px)
+
+
+# ---- seeded ragged batches, every flavour ------------------------------------------------------------
+@pytest.mark.parametrize("p", T.all_params(), ids=T.pname)
+def test_ragged_batch_encode_decode(codec, p):
+    buf, off = T.make_batch(1234 + p.code_size * 4 + p.big_endian * 2 + p.tiff_early_change,
+                            96, T.max_symbol(p))
+    out, out_off, out_len, status, detail = codec.encode_batch(gp(p), buf, off)
+    o_out, o_len, o_st, o_det = O.encode_batch(p, buf, off, out_off)
+    assert np.array_equal(status, o_st) and np.array_equal(detail, o_det)
+    assert np.array_equal(out_len, o_len)
+    assert T.slots_equal(out, o_out, out_off, out_len) < 0
+    dense, doff = T.pack_dense(out, out_off, out_len)
+    # decode into slots two bytes larger than needed
+    cap = np.zeros(off.size, dtype=np.uint64)
+    cap[1:] = np.cumsum(np.diff(off) + np.uint64(2))
+    dec, dlen, dst, ddet = codec.decode_batch(gp(p), dense, doff, cap)
+    o_dec, o_dlen, o_dst, o_ddet = O.decode_batch(p, dense, doff, cap)
+    assert np.array_equal(dst, o_dst) and np.array_equal(ddet, o_ddet) and np.array_equal(dlen, o_dlen)
+    assert T.slots_equal(dec, o_dec, cap, dlen) < 0
+    # round trip wherever the reference's own decoder accepts its encoder's output
+    for i in np.nonzero(o_dst == 0)[0]:
+        a, b = int(cap[i]), int(off[i])
+        l = int(off[i + 1] - off[i])
+        assert np.array_equal(dec[a:a + l], buf[b:b + l])
+
+
+def test_long_streams_with_dictionary_resets(codec):
+    rng = np.random.default_rng(7)
+    for p, n in [(O.tiff(), 200_000), (O.gif(8), 150_000), (O.gif(2), 120_000), (O.fixed(True), 100_000),
+                 (O.variable(5, True, False), 90_000)]:
+        for kind in ("random", "walk", "runs", "zeros"):
+            data = T.make_stream(rng, kind, n, T.max_symbol(p)).tobytes()
+            want = O.encode(p, data)
+            got = codec.encode(gp(p), data)
+            assert got == want, (T.pname(p), kind)
+            assert codec.decode(gp(p), got[2]) == O.decode(p, want[2]), (T.pname(p), kind)
+
+
+# ---- edge cases of the encoder ------------------------------------------------------------------------
+@pytest.mark.parametrize("p", T.all_params(), ids=T.pname)
+def test_encoder_edges(codec, p):
+    hi = T.max_symbol(p)
+    for data in (b"", bytes([0]), bytes([hi]), bytes([hi, hi]), bytes([0, hi, 0, hi, hi, hi, hi])):
+        assert codec.encode(gp(p), data) == O.encode(p, data)
+    if p.flavour == 0 and p.code_size < 8:
+        # unchecked first byte (encoder.rs:311): treated as a node, masked, or a reference panic
+        clear = 1 << p.code_size
+        for data in (bytes([200]), bytes([200, 1]), bytes([200, 255]), bytes([clear, 1, 1, clear & hi]),
+                     bytes([clear + 1, 0, 0, 0, 0]), bytes([clear, clear]), bytes([0, 0, hi + 1]),
+                     bytes([clear + 2, 0]), bytes([clear + 2])):
+            assert codec.encode(gp(p), data) == O.encode(p, data), data
+
+
+@pytest.mark.parametrize("p", [O.gif(8), O.tiff(), O.gif(3), O.fixed(False), O.fixed(True)], ids=T.pname)
+def test_encoder_output_slot_too_small(codec, p):
+    """`&mut [u8]` writer semantics: fill the slot, then Io(WriteZero)."""
+    rng = np.random.default_rng(5)
+    data = T.make_stream(rng, "walk", 3000, T.max_symbol(p)).tobytes()
+    full = O.encode(p, data)[2]
+    for cap in [0, 1, 2, 3, 7, 100, len(full) - 2, len(full) - 1, len(full), len(full) + 1]:
+        assert codec.encode(gp(p), data, cap=cap) == O.encode(p, data, cap=cap), cap
+    # an input error that comes before / after the slot fills up
+    if p.flavour == 0 and p.code_size < 8:
+        bad = bytearray(data)
+        bad[1500] = 255
+        for cap in [10, 600, 5000]:
+            assert codec.encode(gp(p), bytes(bad), cap=cap) == O.encode(p, bytes(bad), cap=cap), cap
+
+
+# ---- decoder error parity --------------------------------------------------------------------------------
+def _mutations(rng, packed: bytes, count: int):
+    yield packed
+    for cut in sorted(set(int(x) for x in rng.integers(0, len(packed), size=count))):
+        yield packed[:cut]                                   # truncated: Io(UnexpectedEof) or worse
+    for _ in range(count):
+        b = bytearray(packed)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+        yield bytes(b)                                       # bit flips: any decoder error, stale-table paths
+    for _ in range(count // 2):
+        yield bytes(rng.integers(0, 256, size=int(rng.integers(1, 400)), dtype=np.uint8))  # garbage
+
+
+@pytest.mark.parametrize("p", [O.gif(8), O.tiff(), O.gif(2), O.gif(5), O.variable(4, True, True),
+                               O.fixed(False), O.fixed(True)], ids=T.pname)
+def test_decoder_error_parity_on_corrupt_streams(codec, p):
+    rng = np.random.default_rng(99 + p.code_size)
+    hi = T.max_symbol(p)
+    streams = []
+    for kind, n in (("text", 5000), ("runs", 9000), ("random", 2500)):
+        packed = O.encode(p, T.make_stream(rng, kind, n, hi).tobytes())[2]
+        streams += list(_mutations(rng, packed, 24))
+    off = np.zeros(len(streams) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s in streams])
+    buf = np.frombuffer(b"".join(streams), dtype=np.uint8)
+    # generous slots: corrupt streams may expand a lot
+    cap = (np.arange(len(streams) + 1, dtype=np.uint64)) * np.uint64(1 << 17)
+    dec, dlen, dst, ddet = codec.decode_batch(gp(p), buf, off, cap)
+    o_dec, o_dlen, o_dst, o_ddet = O.decode_batch(p, buf, off, cap)
+    assert np.array_equal(dst, o_dst)
+    assert np.array_equal(ddet, o_ddet)
+    assert np.array_equal(dlen, o_dlen)
+    assert T.slots_equal(dec, o_dec, cap, dlen) < 0
+    assert len(set(dst.tolist())) >= (3 if p.flavour == 0 else 2)   # several outcomes are exercised
+
+
+def test_decoder_missing_clear_code(codec):
+    """decoder.rs:281-283: a stream that keeps going after the table is full."""
+    # 12-bit codes for 'a' forever, LSB first, cs=8: clear, then 4000 literal codes
+    codes = [256] + [97] * 4000
+    widths = []
+    nxt, w = 258, 9
+    for i, _ in enumerate(codes):
+        widths.append(w)
+        if i >= 2:
+            nxt += 1
+            if nxt == (1 << w) and w < 12:
+                w += 1
+    packed = O.bitwrite(False, codes, widths)
+    want = O.decode(O.gif(8), packed)
+    assert want[0] == O.ERR_MISSING_CLEAR_CODE
+    assert codec.decode(gp(O.gif(8)), packed) == want
+
+
+def test_decoder_self_inconsistent_streams(codec):
+    """encoder output the reference's own decoder rejects; parity is on the result."""
+    rng = np.random.default_rng(11)
+    seen = set()
+    for p in (O.tiff(), O.gif(8), O.gif(3), O.variable(8, True, False), O.variable(6, False, True)):
+        # final dictionary size == 2^w - inc  <=>  n such that (first + n - 1) hits the mask
+        for w in range(p.code_size + 1, 12):
+            n = (1 << w) - (1 if p.tiff_early_change else 0) - ((1 << p.code_size) + 2) + 1
+            for _ in range(3):
+                # distinct-pair data so that every byte after the first adds an entry
+                data = T.make_stream(rng, "random", n, T.max_symbol(p)).tobytes()
+                packed = O.encode(p, data)[2]
+                want = O.decode(p, packed)
+                seen.add(want[0])
+                assert codec.decode(gp(p), packed) == want
+    assert len(seen) >= 2
+
+
+def test_decoder_output_slot_too_small(codec):
+    rng = np.random.default_rng(3)
+    for p in (O.tiff(), O.gif(4), O.fixed(False)):
+        data = T.make_stream(rng, "runs", 4000, T.max_symbol(p)).tobytes()
+        packed = O.encode(p, data)[2]
+        for cap in (0, 1, 2, 17, 1000, 3999, 4000, 4001):
+            assert codec.decode(gp(p), packed, cap=cap) == O.decode(p, packed, cap=cap), cap
+
+
+def test_decoded_size_prepass(codec, lorem_encoded):
+    assert codec.decoded_size(gp(O.gif(7)), lorem_encoded) == (0, 0, 23336)
+    assert codec.decoded_size(gp(O.tiff()), T.BAD_TIFF) == O.decoded_size(O.tiff(), T.BAD_TIFF)
+
+
+# ---- batch plumbing ------------------------------------------------------------------------------------------
+def test_per_stream_code_size(codec):
+    rng = np.random.default_rng(21)
+    cs = (2 + np.arange(40) % 7).astype(np.uint8)
+    streams = [T.make_stream(rng, T.KINDS[i % 6], int(rng.integers(0, 5000)), (1 << int(cs[i])) - 1) for i in range(40)]
+    off = np.zeros(41, dtype=np.uint64)
+    off[1:] = np.cumsum([s.size for s in streams])
+    buf = np.concatenate(streams)
+    out, out_off, out_len, status, detail = codec.encode_batch(gp(O.gif(8)), buf, off, code_size=cs)
+    o_out, o_len, o_st, o_det = O.encode_batch(O.gif(8), buf, off, out_off, code_size=cs)
+    assert np.array_equal(status, o_st) and np.array_equal(out_len, o_len)
+    assert T.slots_equal(out, o_out, out_off, out_len) < 0
+    dense, doff = T.pack_dense(out, out_off, out_len)
+    dec, dlen, dst, _ = codec.decode_batch(gp(O.gif(8)), dense, doff, off, code_size=cs)
+    o_dec, o_dlen, o_dst, _ = O.decode_batch(O.gif(8), dense, doff, off, code_size=cs)
+    assert np.array_equal(dst, o_dst) and np.array_equal(dlen, o_dlen)
+    assert T.slots_equal(dec, o_dec, off, dlen) < 0
+
+
+def test_device_pointer_api_and_compaction(codec):
+    """Device-resident batch through torch tensors + the compaction stage, on a side stream."""
+    import torch
+    from lzw_b200 import workloads as W
+    buf, off = W.tiff_strips(256, seed=77)
+    slots = W.encode_slots(off)
+    n = off.size - 1
+    dev = torch.device("cuda:0")
+    t_in = torch.from_numpy(buf).to(dev)
+    t_off = torch.from_numpy(off.view(np.int64)).to(dev)
+    t_slots = torch.from_numpy(slots.view(np.int64)).to(dev)
+    t_out = torch.zeros(int(slots[-1]), dtype=torch.uint8, device=dev)
+    t_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    t_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    t_det = torch.zeros(n, dtype=torch.int32, device=dev)
+    t_dense = torch.zeros(int(slots[-1]), dtype=torch.uint8, device=dev)
+    t_doff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        codec.encode_batch_device(gp(O.tiff()), n, t_in.data_ptr(), t_off.data_ptr(), t_out.data_ptr(),
+                                  t_slots.data_ptr(), t_len.data_ptr(), t_st.data_ptr(), t_det.data_ptr(),
+                                  stream=stream.cuda_stream)
+        codec.compact_device(t_out.data_ptr(), t_slots.data_ptr(), t_len.data_ptr(), n,
+                             t_dense.data_ptr(), t_doff.data_ptr(), align=1, stream=stream.cuda_stream)
+    stream.synchronize()
+    o_out, o_len, o_st, _ = O.encode_batch(O.tiff(), buf, off, slots, threads=4)
+    assert np.array_equal(t_len.cpu().numpy().astype(np.uint64), o_len)
+    assert (t_st.cpu().numpy() == 0).all()
+    dense, doff = T.pack_dense(o_out, slots, o_len)
+    assert np.array_equal(t_doff.cpu().numpy().astype(np.uint64), doff)
+    assert np.array_equal(t_dense.cpu().numpy()[:dense.size], dense)
+    # decode the dense buffer back on the device
+    t_dec = torch.zeros(buf.size, dtype=torch.uint8, device=dev)
+    with torch.cuda.stream(stream):
+        codec.decode_batch_device(gp(O.tiff()), n, t_dense.data_ptr(), t_doff.data_ptr(), t_dec.data_ptr(),
+                                  t_off.data_ptr(), t_len.data_ptr(), t_st.data_ptr(), t_det.data_ptr(),
+                                  stream=stream.cuda_stream)
+    stream.synchronize()
+    st = t_st.cpu().numpy()
+    o_dec, o_dlen, o_dst, _ = O.decode_batch(O.tiff(), dense, doff, off, threads=4)
+    assert np.array_equal(st.astype(np.uint32), o_dst)
+    ok = o_dst == 0
+    got = t_dec.cpu().numpy()
+    for i in np.nonzero(ok)[0]:
+        assert np.array_equal(got[int(off[i]):int(off[i + 1])], buf[int(off[i]):int(off[i + 1])])
+
+
+def test_encode_batch_dense_host_api(codec):
+    """slzw_encode_batch_host_dense: strips back to back, offsets returned, only encoded bytes copied."""
+    buf, off = T.make_batch(4242, 300, 255, max_len=20000)
+    for align in (1, 2):
+        dense, doff, st, det = codec.encode_batch_dense(gp(O.tiff()), buf, off, align=align)
+        slots = np.zeros(off.size, dtype=np.uint64)
+        slots[1:] = np.cumsum(np.diff(off) * np.uint64(2) + np.uint64(16))
+        o_out, o_len, o_st, o_det = O.encode_batch(O.tiff(), buf, off, slots)
+        assert np.array_equal(st, o_st) and np.array_equal(det, o_det)
+        padded = (o_len + np.uint64(align - 1)) // np.uint64(align) * np.uint64(align)
+        assert np.array_equal(np.diff(doff), padded)
+        for i in range(o_len.size):
+            assert np.array_equal(dense[int(doff[i]):int(doff[i]) + int(o_len[i])],
+                                  o_out[int(slots[i]):int(slots[i]) + int(o_len[i])]), i
+
+
+def test_compaction_alignment(codec):
+    import torch
+    rng = np.random.default_rng(5)
+    n = 300
+    lens = rng.integers(0, 900, size=n).astype(np.uint64)
+    src_off = np.zeros(n + 1, dtype=np.uint64)
+    src_off[1:] = np.cumsum(lens + rng.integers(0, 7, size=n).astype(np.uint64))
+    src = rng.integers(0, 256, size=int(src_off[-1]) + 8, dtype=np.uint8)
+    dev = torch.device("cuda:0")
+    for align in (1, 2, 16):
+        t_src = torch.from_numpy(src).to(dev)
+        t_so = torch.from_numpy(src_off.view(np.int64)).to(dev)
+        t_len = torch.from_numpy(lens.view(np.int64)).to(dev)
+        t_dst = torch.zeros(int(src_off[-1]) + 16 * n, dtype=torch.uint8, device=dev)
+        t_do = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        codec.compact_device(t_src.data_ptr(), t_so.data_ptr(), t_len.data_ptr(), n, t_dst.data_ptr(),
+                             t_do.data_ptr(), align=align)
+        torch.cuda.synchronize()
+        do = t_do.cpu().numpy().astype(np.uint64)
+        padded = (lens + np.uint64(align - 1)) // np.uint64(align) * np.uint64(align)
+        want = np.zeros(n + 1, dtype=np.uint64)
+        want[1:] = np.cumsum(padded)
+        assert np.array_equal(do, want)
+        dst = t_dst.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(dst[int(do[i]):int(do[i]) + int(lens[i])],
+                                  src[int(src_off[i]):int(src_off[i]) + int(lens[i])]), (align, i)
+
+
+def test_config3_scaled_down_vs_oracle(codec):
+    """BASELINE config 3 at 2,048 strips: byte-exact against the oracle, then decode."""
+    from lzw_b200 import workloads as W
+    buf, off = W.tiff_strips(2048)
+    out, out_off, out_len, status, detail = codec.encode_batch(gp(O.tiff()), buf, off)
+    o_out, o_len, o_st, _ = O.encode_batch(O.tiff(), buf, off, out_off, threads=8)
+    assert np.array_equal(status, o_st) and np.array_equal(out_len, o_len)
+    assert T.slots_equal(out, o_out, out_off, out_len) < 0
+    dense, doff = T.pack_dense(out, out_off, out_len)
+    dec, dlen, dst, ddet = codec.decode_batch(gp(O.tiff()), dense, doff, off)
+    o_dec, o_dlen, o_dst, o_ddet = O.decode_batch(O.tiff(), dense, doff, off, threads=8)
+    assert np.array_equal(dst, o_dst) and np.array_equal(ddet, o_ddet) and np.array_equal(dlen, o_dlen)
+    assert T.slots_equal(dec, o_dec, off, dlen) < 0
+    ok = dst == 0
+    assert ok.mean() > 0.95
+    for i in np.nonzero(ok)[0]:
+        assert np.array_equal(dec[int(off[i]):int(off[i + 1])], buf[int(off[i]):int(off[i + 1])])
