@@ -16,7 +16,7 @@
 
 namespace slzw {
 // encode_kernels.cu
-size_t encode_smem_bytes();
+void encode_select_config(int c);
 int encode_warps_per_cta();
 cudaError_t encode_configure();
 cudaError_t encode_launch(const DevBatch& a, int grid, cudaStream_t stream);
@@ -395,6 +395,7 @@ int slzw_create(int device, slzw_ctx** out) {
     if (!ctx) return SLZW_RC_NOMEM;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char* e = getenv("SLZW_ENC_CONFIG")) encode_select_config(atoi(e));  // tuning knob
     DeviceGuard guard(device);
     if (!guard.ok || encode_configure() != cudaSuccess || decode_exact_configure() != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {

@@ -1,0 +1,61 @@
+"""Runs a few encode / compact / decode passes on a small config-3 batch (for ncu captures)."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--streams", type=int, default=2048)
+    ap.add_argument("--passes", type=int, default=2)
+    ap.add_argument("--what", default="all", choices=["all", "encode", "decode"])
+    args = ap.parse_args()
+    import torch
+
+    import lzw_b200
+    from lzw_b200 import workloads as W
+    from lzw_b200.types import tiff_params
+
+    dev = torch.device("cuda:0")
+    codec = lzw_b200.Codec(0)
+    p = tiff_params()
+    buf, off = W.tiff_strips(args.streams)
+    slots = W.encode_slots(off)
+    n = off.size - 1
+    i64 = lambda a: torch.from_numpy(a.view(np.int64)).to(dev)
+    t_in, t_off, t_slots = torch.from_numpy(buf).to(dev), i64(off), i64(slots)
+    t_enc = torch.empty(int(slots[-1]), dtype=torch.uint8, device=dev)
+    t_len = torch.zeros(n, dtype=torch.int64, device=dev)
+    t_st = torch.zeros(n, dtype=torch.int32, device=dev)
+    t_det = torch.zeros(n, dtype=torch.int32, device=dev)
+    t_dense = torch.empty(int(slots[-1]), dtype=torch.uint8, device=dev)
+    t_doff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    t_dec = torch.empty(buf.size, dtype=torch.uint8, device=dev)
+    for _ in range(args.passes):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        codec.encode_batch_device(p, n, t_in.data_ptr(), t_off.data_ptr(), t_enc.data_ptr(), t_slots.data_ptr(),
+                                  t_len.data_ptr(), t_st.data_ptr(), t_det.data_ptr())
+        ev[1].record()
+        codec.compact_device(t_enc.data_ptr(), t_slots.data_ptr(), t_len.data_ptr(), n, t_dense.data_ptr(),
+                             t_doff.data_ptr())
+        ev[2].record()
+        if args.what != "encode":
+            codec.decode_batch_device(p, n, t_dense.data_ptr(), t_doff.data_ptr(), t_dec.data_ptr(), t_off.data_ptr(),
+                                      t_len.data_ptr(), t_st.data_ptr(), t_det.data_ptr())
+        ev[3].record()
+        torch.cuda.synchronize()
+        print(f"bytes={buf.size} encode_ms={ev[0].elapsed_time(ev[1]):.3f} compact_ms={ev[1].elapsed_time(ev[2]):.3f} "
+              f"decode_ms={ev[2].elapsed_time(ev[3]):.3f}")
+    if args.what != "encode":
+        print("round trip equal:", bool(torch.equal(t_dec, t_in)))
+    codec.close()
+
+
+if __name__ == "__main__":
+    main()
