@@ -1,16 +1,26 @@
 // encode_kernels.cu -- batched LZW encoder for sm_100a.
 //
-// One warp per stream, persistent CTAs (one per SM), streams handed out through a global work
-// queue in the order chosen by the scheduler.  Per stream:
+// One warp per stream, one persistent CTA of 12 or 13 warps per SM, streams handed out through a
+// global work queue in the order chosen by the scheduler.  Every warp owns one 16 KB dictionary that
+// is 16 KB-ALIGNED in the shared-memory window, so that `table base | slot offset` needs no add:
+// the base is folded into the per-byte hash bits and a probe address is one LOP3 away from the
+// slot word it depends on.  Per stream:
 //   * the reference's arena trie (encoder.rs:58-149) is replaced by an open-addressing hash
 //     dictionary keyed on (prefix code, next byte) -> code, one u32 per slot
-//     [code:12 | prefix:12 | byte:8], resident in shared memory; numbering of new entries is
-//     insertion order and lookups are exact (full linear probing), so the emitted codes equal
-//     the reference's;
-//   * lane 0 walks the input (the match loop is a dependent chain, one probe per byte,
-//     encoder.rs:313-337) over tiles the warp stages into shared memory with cp.async, double
-//     buffered; the loop is software-pipelined and predicated (see match_tile);
-//   * emitted codes are buffered as [width:4 | code:12] and bit-packed by the whole warp
+//     [prefix':12 | byte:8 | code':12], 4096 slots = 16 KB of shared memory.  x' = x * 0x9E5 mod 4096
+//     is a bijection of the 12-bit codes ("scrambled" codes); the slot index is
+//     prefix' ^ (byte * 0x6A7 mod 4096), so the next probe address is a shift and one LOP3 away from
+//     the slot word that was just loaded.  Numbering of new entries is insertion order and lookups
+//     are exact (full linear probing), so the emitted codes equal the reference's;
+//   * the match loop (encoder.rs:313-337) is a dependent chain, one probe per input byte.  It is
+//     executed by all 32 lanes with identical values (no divergence); the probe for byte i+1 is
+//     issued speculatively (assuming byte i hits) before byte i's key comparison resolves, so a
+//     run of hits costs LDS -> SHF -> LOP3 -> LDS per byte;
+//   * everything about an input byte that does not depend on the chain (key bits, hash bits) is
+//     precomputed by the whole warp into a 64-bit record per byte (the input tile never sits in
+//     shared memory as raw bytes; the next tile's words are prefetched into registers while the
+//     current tile is matched);
+//   * emitted codes are buffered as [width:4 | code':12] and bit-packed by the whole warp
 //     (LSB-first like io.rs:234-248 or MSB-first like io.rs:296-311) into a shared-memory word
 //     window that is written to the output slot with aligned 32-bit stores;
 //   * the dictionary reset (encoder.rs:329-333) is a cooperative vectorised clear.
@@ -23,49 +33,37 @@ namespace slzw {
 
 namespace {
 
-// Dictionary slot = [code:12 | prefix code:12 | byte:8]; 0 = empty (codes start at >= 6).
-// The low 20 bits are the key (prefix code << 8 | byte); the slot index is a multiplicative
-// hash of the key.
-constexpr uint32_t kHashA = 0x9E3779B1u;
+constexpr int kSlots = 4096;
+constexpr uint32_t kIdxMask4 = (uint32_t)(kSlots - 1) << 2;  // byte offset of a slot
+constexpr uint32_t kScr = 0x9E5u;     // code -> code' = code * kScr mod 4096 (odd => bijection)
+constexpr uint32_t kScrInv = 0xBEDu;  // kScr * kScrInv == 1 mod 4096
+constexpr uint32_t kByteMul = 0x6A7u; // byte -> hash contribution
+static_assert(((kScr * kScrInv) & 0xFFFu) == 1u, "kScrInv must invert kScr mod 4096");
 
-template <int SLOTS>
-__device__ __forceinline__ uint32_t slot_of_key(uint32_t key) {  // key = prefix code << 8 | byte
-    const uint32_t x = key * kHashA;
-    if constexpr ((SLOTS & (SLOTS - 1)) == 0) {
-        return x >> (32 - __builtin_ctz(SLOTS));
-    } else {
-        return __umulhi(x, (uint32_t)SLOTS);
-    }
-}
+__device__ __forceinline__ uint32_t scr(uint32_t code) { return (code * kScr) & 0xFFFu; }
+__device__ __forceinline__ uint32_t unscr(uint32_t code) { return (code * kScrInv) & 0xFFFu; }
 
-// Shared-memory accesses by 32-bit shared address (no generic-address conversion in the loop).
-__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+// Dictionary accesses by 32-bit shared-window address.  They are volatile asm statements so that
+// the compiler keeps them exactly where the match loop puts them (in particular the speculative
+// probe stays ahead of the branch it speculates on) and in order with each other.
+__device__ __forceinline__ uint32_t tbl_ld(uint32_t saddr) {
     uint32_t v;
-    asm volatile("ld.volatile.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
-    uint32_t v;
-    asm("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(saddr));  // input tile: read-only here
-    return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t saddr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(saddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
-    asm volatile("st.shared.u16 [%0], %1;\n" ::"r"(saddr), "h"((uint16_t)v) : "memory");
+__device__ __forceinline__ void tbl_st(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(saddr), "r"(v));
 }
 
-enum Reason : uint32_t { R_TILE_END = 0, R_RESET = 1, R_STOP = 2 };
-
-template <int SLOTS, int TILE>
-struct EncWarpSmem {
+// Per-warp working set besides the dictionary.
+template <int TILE>
+struct EncMisc {
+    static constexpr int kRecs = TILE + 8;                      // + lookahead padding
     static constexpr int kCodeBuf = TILE + 16;                  // codes one tile can emit
     static constexpr int kOutWords = (kCodeBuf * 12) / 32 + 4;  // packed window
-    uint32_t table[SLOTS];
+    uint2 rec[kRecs];          // per input byte: {byte << 12, hash bits | table base}
     uint32_t outw[kOutWords];
-    uint16_t codes[kCodeBuf];
-    __align__(16) uint8_t tile[2][TILE + 32];  // double-buffered input tiles
+    uint16_t codes[kCodeBuf];  // [width:4 | code':12]
 };
 
 // Writes one 32-bit word of the packed window to the output slot.  Word `gw` covers stream
@@ -85,186 +83,173 @@ __device__ __forceinline__ void store_word(uint8_t* dst, uint32_t mis, uint64_t 
     }
 }
 
-// Lane-0 match state (encoder.rs:289-311), kept in registers across tiles.
+// Match state (encoder.rs:289-311), identical in every lane, kept in registers across tiles.
 struct MatchState {
-    uint32_t pw;          // current_prefix << 20
-    uint32_t next_code;   // tree.len()
-    uint32_t write_size;  // encoder.rs:289
-    uint32_t mask;        // size_increase_mask, encoder.rs:292
-    uint32_t ncodes;      // codes buffered for the packer
-    uint32_t status, detail;
+    uint32_t t;       // current_prefix' << 20 (scrambled prefix in key position)
+    uint32_t ncs;     // tree.len()' (scrambled next code)
+    uint32_t ws;      // write_size, encoder.rs:289
+    uint32_t mask;    // size_increase_mask, encoder.rs:292
+    uint32_t until;   // inserts left until the next width bump / reset (variable) or until the
+                      // table is full (fixed)
+    uint32_t ncodes;  // codes buffered for the packer
 };
 
-// Collision path of the dictionary lookup.  The first probe (slot `a`, word `s`) was neither
-// the key nor empty.  Every lane of the warp then looks at one of the next 32 slots of the
-// linear-probing sequence; two ballots give the first matching and the first empty slot, and
-// whichever comes first decides (an entry is never stored past an empty slot of its own probe
-// sequence).  One shared-memory wavefront resolves what would be up to 32 dependent probes, which
-// is what lets the table run at a load factor of 0.94 (4096 slots for <= 3838 entries).
-// Returns hit; `a` = shared address of the matching or of the empty slot, `s` = its word.
-template <int SLOTS>
+// Collision path of the dictionary lookup.  The home slot (address `a`) held another key.
+// Every lane of the warp then looks at one of the next 32 slots of the linear-probing sequence;
+// two ballots give the first matching and the first empty slot, and whichever comes first decides
+// (an entry is never stored past an empty slot of its own probe sequence).  One shared-memory
+// wavefront resolves what would be up to 32 dependent probes, which is what lets the table run at
+// a load factor of 0.94 (4096 slots for <= 3838 entries).
+// Returns hit; `a` = address of the matching or of the empty slot, `s` = its word.
 __device__ __forceinline__ bool probe_wide(uint32_t tb, uint32_t key, int lane, uint32_t& a,
                                            uint32_t& s) {
-    static_assert((SLOTS & (SLOTS - 1)) == 0, "wide probing needs a power-of-two table");
-    uint32_t h = ((a - tb) >> 2) + 1u;  // first slot of the window
+    uint32_t h4 = a + 4u * (uint32_t)(lane + 1);  // this lane's slot in the first window
     // the table always keeps empty slots (<= 4091 entries); the bound only keeps a corrupted
     // table from hanging the warp
-    for (int round = 0; round < SLOTS / kWarpSize + 1; round++) {
-        const uint32_t sa = tb + 4u * ((h + (uint32_t)lane) & (uint32_t)(SLOTS - 1));
-        const uint32_t v = lds_u32(sa);
-        const uint32_t bm = __ballot_sync(kFullMask, (v & 0xFFFFFu) == key && v != 0u);
+    for (int round = 0; round < kSlots / kWarpSize + 1; round++) {
+        const uint32_t v = tbl_ld(tb | (h4 & kIdxMask4));
+        const uint32_t bm = __ballot_sync(kFullMask, ((v ^ key) >> 12) == 0u && v != 0u);
         const uint32_t be = __ballot_sync(kFullMask, v == 0u);
         const uint32_t stop = bm | be;
         if (stop) {
             const int pos = __ffs(stop) - 1;
-            a = tb + 4u * ((h + (uint32_t)pos) & (uint32_t)(SLOTS - 1));
+            a = tb | (__shfl_sync(kFullMask, h4, pos) & kIdxMask4);
             s = __shfl_sync(kFullMask, v, pos);
             return (bm >> pos) & 1u;
         }
-        h += kWarpSize;
+        h4 += 4u * kWarpSize;
     }
     s = 0u;
     return false;
 }
 
-// The match loop of encoder.rs:313-337 / 639-651 over one staged tile, executed by every lane of
-// the warp with identical values (warp-uniform control flow: a diverged warp pays ~20 cycles
-// per branch, profiles/r01_encode_ncu.md).
-//
-// ncu on the first versions showed the loop is bound by instruction issue of a single warp
-// (about 6 cycles per issued instruction, profiles/r01_encode_v2_ncu.txt), not by shared-memory
-// latency, so the loop is written for the fewest instructions per input byte: one probe per
-// byte, the prefix carried pre-shifted (`ph` = code << 8, so key = ph | byte), four bytes per
-// trip, everything that is not hit / clean miss out of line.
-// GUARD adds the `&mut [u8]`-writer capacity check; it is only instantiated for tiles that
-// could overflow the output slot (`room` = bits the writer still accepts).
-template <int SLOTS, bool CHECK, bool FIXED, bool GUARD>
-__device__ __forceinline__ uint32_t match_tile(uint32_t* __restrict__ table,
-                                               uint16_t* __restrict__ codes, const int lane,
-                                               const uint8_t* __restrict__ t, uint32_t& i_io,
-                                               const uint32_t len, MatchState& m, int32_t room,
-                                               const uint32_t max_code, const uint32_t first_code,
-                                               const uint32_t clear_code, const uint32_t cs,
-                                               const uint32_t inc) {
-    if (i_io >= len) return R_TILE_END;
-    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(table);
-    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(codes);
-    const uint32_t t0 = (uint32_t)__cvta_generic_to_shared(t);
-    uint32_t tp = t0 + i_io;         // shared address of the next input byte
-    const uint32_t te = t0 + len;    // end of the tile
-    uint32_t cp = cbase + 2u * m.ncodes;
-    uint32_t ph = (m.pw >> 20) << 8;  // current_prefix, pre-shifted into key position
-    uint32_t nh = m.next_code << 20;  // tree.len(), pre-shifted into slot position
-    uint32_t ws = FIXED ? 12u : m.write_size;
-    uint32_t wtag = ws << 12;
-    uint32_t mask = m.mask;
-    // inserts left before something happens: width bump / reset (variable), table full (fixed)
-    uint32_t until = FIXED ? 4096u - m.next_code : mask - m.next_code + 1u;
-    uint32_t reason = R_TILE_END;
-
-    // One byte of encoder.rs:313-337.  `continue`-style flow is done with gotos so that the
-    // four unrolled copies share the out-of-line blocks' code shape.
-#define SLZW_STEP(OFF, K)                                                                       \
-    {                                                                                           \
-        const uint32_t k = (K);                                                                 \
-        if (CHECK && k > max_code) { /* encoder.rs:315-317 */                                   \
-            m.status = SLZW_ERR_UNEXPECTED_CODE;                                                \
-            m.detail = k;                                                                       \
-            reason = R_STOP;                                                                    \
-            tp += OFF;                                                                          \
-            goto done;                                                                          \
-        }                                                                                       \
-        const uint32_t key = ph | k;                                                            \
-        uint32_t a = tb + 4u * slot_of_key<SLOTS>(key);                                         \
-        uint32_t s = lds_u32(a);                                                                \
-        if ((s & 0xFFFFFu) == key && s != 0u) { /* find_word hit, encoder.rs:319-320 */         \
-            ph = (s >> 12) & 0xFFF00u;                                                          \
-        } else {                                                                                \
-            bool hit = false;                                                                   \
-            if (s != 0u) hit = probe_wide<SLOTS>(tb, key, lane, a, s);                          \
-            if (hit) {                                                                          \
-                ph = (s >> 12) & 0xFFF00u;                                                      \
-            } else {                                                                            \
-                /* miss: encoder.rs:322-324 / 645-649 */                                        \
-                sts_u16(cp, (ph >> 8) | wtag);                                                  \
-                cp += 2u;                                                                       \
-                ph = k << 8;                                                                    \
-                if (GUARD) room -= (int32_t)ws;                                                 \
-                if (!FIXED || until != 0u) {                                                    \
-                    sts_u32(a, nh | key);                                                       \
-                    nh += 1u << 20;                                                             \
-                    until--;                                                                    \
-                    if (!FIXED && until == 0u) { /* new index == mask, encoder.rs:326 */        \
-                        tp += OFF + 1;                                                          \
-                        goto bump;                                                              \
-                    }                                                                           \
-                }                                                                               \
-                if (GUARD && room < 0) {                                                        \
-                    tp += OFF + 1;                                                              \
-                    goto full;                                                                  \
-                }                                                                               \
-            }                                                                                   \
-        }                                                                                       \
-    }
-
-    for (;;) {
-        while (tp + 4u <= te) {
-            // the four input bytes are fetched up front so their latency is off the chain
-            const uint32_t b0 = lds_u8(tp), b1 = lds_u8(tp + 1), b2 = lds_u8(tp + 2),
-                           b3 = lds_u8(tp + 3);
-            SLZW_STEP(0, b0)
-            SLZW_STEP(1, b1)
-            SLZW_STEP(2, b2)
-            SLZW_STEP(3, b3)
-            tp += 4u;
-        }
-        while (tp < te) {
-            SLZW_STEP(0, lds_u8(tp))
-            tp += 1u;
-        }
-        break;
-    bump:
-        if (GUARD && room < 0) goto full;
-        if (ws < 12u) {  // encoder.rs:327-328
-            ws++;
-            wtag = ws << 12;
-            mask = (1u << ws) - inc;
-            until = mask - (nh >> 20) + 1u;
-            continue;
-        }
-        // encoder.rs:329-333: clear code at 12 bits, dictionary restarts
-        sts_u16(cp, clear_code | (12u << 12));
-        cp += 2u;
-        ws = cs + 1;
-        mask = (1u << ws) - inc;
-        nh = first_code << 20;
-        until = mask - first_code + 1u;
-        if (GUARD && room - 12 < 0) goto full_noinc;
-        reason = R_RESET;
-        break;
-    full:  // the writer is full (io.rs:244 / 307)
-    full_noinc:
-        m.status = SLZW_ERR_IO_WRITE_ZERO;
-        reason = R_STOP;
-        break;
-    }
-done:
-#undef SLZW_STEP
-    m.ncodes = (cp - cbase) >> 1;
-    // nh wraps at code 4096 (reachable for one step with the default strategy), so the count
-    // is derived from `until`, which is exact
-    m.next_code = FIXED ? 4096u - until : mask + 1u - until;
-    m.write_size = ws;
-    m.mask = mask;
-    m.pw = (ph >> 8) << 20;
-    i_io = tp - t0;
-    return reason;
+__device__ __forceinline__ void clear_table(uint32_t* table, int lane) {
+#pragma unroll 4
+    for (int j = lane; j < kSlots / 4; j += kWarpSize)
+        reinterpret_cast<uint4*>(table)[j] = make_uint4(0, 0, 0, 0);
 }
 
-template <int SLOTS, int TILE>
-__device__ void encode_stream(const DevBatch& a, uint32_t sid, EncWarpSmem<SLOTS, TILE>& S,
-                              int lane) {
-    using Smem = EncWarpSmem<SLOTS, TILE>;
+// The match loop of encoder.rs:313-337 / 639-651 over the `len` byte records of one tile.
+// rec[i] = {byte << 12, table base | hash contribution of the byte as a slot byte offset}.
+// Executed by every lane with identical values.  The loop never leaves the tile early: input
+// validation truncates the tile beforehand and the capacity check happens per tile (see
+// encode_stream).
+template <bool FIXED>
+__device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const uint32_t tb,
+                                           const uint2* __restrict__ rec,
+                                           uint16_t* __restrict__ codes, const int lane,
+                                           const uint32_t len, MatchState& m, const uint32_t cs,
+                                           const uint32_t inc, const uint32_t clear_code,
+                                           const uint32_t first_code) {
+    uint32_t t = m.t;
+    uint32_t ncs = m.ncs;
+    uint32_t ws = FIXED ? 12u : m.ws;
+    uint32_t wtag = ws << 12;
+    uint32_t mask = m.mask;
+    uint32_t until = m.until;
+    uint32_t cp = m.ncodes;
+
+    uint2 r0 = rec[0];
+    uint32_t a = (t >> 18) ^ r0.y;  // home slot of (prefix, byte 0); t >> 18 == prefix' << 2
+    uint32_t s = tbl_ld(a);
+
+    // One byte of encoder.rs:313-337.  RC = record of this byte, RN = record of the next byte
+    // (anything addressable when this is the last byte of the tile: the lookahead is discarded).
+    // On entry `s` is the word of the home slot `a` of the key (t, RC).
+#define SLZW_STEP(RC, RN)                                                                       \
+    {                                                                                           \
+        const uint32_t an = ((s << 2) & kIdxMask4) ^ (RN).y;                                    \
+        const uint32_t sn = tbl_ld(an);    /* speculative: assumes this byte hits */            \
+        const uint32_t x = s ^ t ^ (RC).x; /* == code' iff the slot holds this key */           \
+        if (x - 1u < 4095u) {              /* find_word hit, encoder.rs:319-320 */              \
+            t = s << 20;                                                                        \
+            s = sn;                                                                             \
+            a = an;                                                                             \
+        } else {                                                                                \
+            const uint32_t key = t | (RC).x;                                                    \
+            bool hit = false;                                                                   \
+            if (s != 0u) hit = probe_wide(tb, key, lane, a, s);                                 \
+            if (hit) {                                                                          \
+                t = s << 20;                                                                    \
+            } else {                                                                            \
+                /* miss: encoder.rs:322-324 / 645-649 */                                        \
+                codes[cp++] = (uint16_t)((t >> 20) | wtag);                                     \
+                if (!FIXED || until != 0u) {                                                    \
+                    tbl_st(a, key | ncs);                                                       \
+                    ncs = (ncs + kScr) & 0xFFFu;                                                \
+                    until--;                                                                    \
+                    if (!FIXED && until == 0u) { /* new index == mask, encoder.rs:326 */        \
+                        if (ws < 12u) {          /* encoder.rs:327-328 */                       \
+                            ws++;                                                               \
+                            wtag = ws << 12;                                                    \
+                            const uint32_t nm = (1u << ws) - inc;                               \
+                            until = nm - mask;                                                  \
+                            mask = nm;                                                          \
+                        } else { /* encoder.rs:329-333: clear at 12 bits, dictionary restarts */ \
+                            codes[cp++] = (uint16_t)(scr(clear_code) | (12u << 12));            \
+                            ws = cs + 1u;                                                       \
+                            wtag = ws << 12;                                                    \
+                            mask = (1u << ws) - inc;                                            \
+                            until = mask - first_code + 1u;                                     \
+                            ncs = scr(first_code);                                              \
+                            __syncwarp();                                                       \
+                            clear_table(table, lane);                                           \
+                            __syncwarp();                                                       \
+                        }                                                                       \
+                    }                                                                           \
+                }                                                                               \
+                t = (RC).x * (kScr << 8); /* prefix = this byte: (k * kScr mod 4096) << 20 */   \
+            }                                                                                   \
+            a = ((t >> 18) & kIdxMask4) ^ (RN).y;                                               \
+            s = tbl_ld(a);                                                                      \
+        }                                                                                       \
+    }
+
+    uint32_t i = 0;
+    while (i + 4u <= len) {
+        const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
+        SLZW_STEP(r0, r1)
+        SLZW_STEP(r1, r2)
+        SLZW_STEP(r2, r3)
+        SLZW_STEP(r3, r4)
+        r0 = r4;
+        i += 4u;
+    }
+    while (i < len) {
+        const uint2 r1 = rec[i + 1];
+        SLZW_STEP(r0, r1)
+        r0 = r1;
+        i += 1u;
+    }
+#undef SLZW_STEP
+
+    m.t = t;
+    m.ncs = ncs;
+    m.ws = ws;
+    m.mask = mask;
+    m.until = until;
+    m.ncodes = cp;
+}
+
+// The 32-bit word of lane `lane` of the tile whose first byte is at `p` (skew = p & 3): the
+// aligned word at p - skew + 4 * lane, or 0 when it holds no byte of [p, p + tile_len).  An
+// aligned word that holds at least one byte of the stream is read whole.
+__device__ __forceinline__ uint32_t load_tile_word(const uint8_t* __restrict__ p, uint32_t skew,
+                                                   uint32_t tile_len, int lane) {
+    const uint32_t lo = 4u * (uint32_t)lane;
+    if (lo + 3u >= skew && lo < skew + tile_len)
+        return __ldg(reinterpret_cast<const uint32_t*>(p - skew + lo));
+    return 0u;
+}
+
+template <int TILE, bool FIXED>
+__device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restrict__ table,
+                              const uint32_t tb, EncMisc<TILE>& S, int lane) {
+    using Misc = EncMisc<TILE>;
+    static_assert(TILE % 4 == 0 && TILE <= 4 * kWarpSize, "one 32-bit word per lane");
+    uint2* __restrict__ rec = S.rec;
+    uint16_t* __restrict__ codes = S.codes;
+    uint32_t* __restrict__ outw = S.outw;
     const uint64_t in_begin = a.in_off[sid];
     const uint64_t n = a.in_off[sid + 1] - in_begin;
     const uint8_t* src = a.in + in_begin;
@@ -275,12 +260,11 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, EncWarpSmem<SLOTS
         dst = a.out + ob;
         cap = a.out_off[sid + 1] - ob;
     }
-    const bool fixed = a.p.flavour == SLZW_FLAVOUR_FIXED;
     const bool big = a.p.big_endian != 0;
-    const uint32_t inc = (!fixed && a.p.tiff_early_change) ? 1u : 0u;
-    uint32_t cs = fixed ? 8u : (a.code_size ? a.code_size[sid] : a.p.code_size);
+    const uint32_t inc = (!FIXED && a.p.tiff_early_change) ? 1u : 0u;
+    const uint32_t cs = FIXED ? 8u : (a.code_size ? a.code_size[sid] : a.p.code_size);
 
-    if (!fixed && (cs < 2 || cs > 8)) {  // encoder.rs:281-283
+    if (!FIXED && (cs < 2 || cs > 8)) {  // encoder.rs:281-283
         if (lane == 0) {
             a.out_len[sid] = 0;
             a.status[sid] = SLZW_ERR_CODE_SIZE;
@@ -289,31 +273,29 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, EncWarpSmem<SLOTS
         return;
     }
 
-    // first input tile in flight while the dictionary is cleared
-    uint64_t pos = n > 0 ? 1 : 0;  // the first byte is consumed below (encoder.rs:311)
-    uint32_t tile_len = (uint32_t)((n - pos) < (uint64_t)TILE ? (n - pos) : TILE);
-    uint32_t skew = 0;
-    int buf = 0;
-    if (tile_len) skew = stage_tile_async(src + pos, tile_len, S.tile[0], lane);
+    // first tile's words in flight while the dictionary is cleared; the first byte of the stream
+    // is consumed below (encoder.rs:311), tiles start at byte 1
+    uint64_t pos = n > 0 ? 1 : 0;
+    uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(src + pos) & 3u);
+    uint32_t tile_len = (uint32_t)((n - pos) < (uint64_t)(TILE - skew) ? (n - pos) : (TILE - skew));
+    uint32_t w = tile_len ? load_tile_word(src + pos, skew, tile_len, lane) : 0u;
 
-    // cooperative clear of the dictionary and the packed window
-    for (int i = lane; i < SLOTS / 4; i += kWarpSize)
-        reinterpret_cast<uint4*>(S.table)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = lane; i < Smem::kOutWords; i += kWarpSize) S.outw[i] = 0;
+    clear_table(table, lane);
+    for (int i = lane; i < Misc::kOutWords; i += kWarpSize) outw[i] = 0;
 
     const uint32_t max_code = (1u << cs) - 1;  // encoder.rs:285
     const uint32_t clear_code = 1u << cs;      // encoder.rs:290
     const uint32_t eoi = clear_code + 1;       // encoder.rs:291
-    const uint32_t first_code = fixed ? 256u : clear_code + 2;
+    const uint32_t first_code = FIXED ? 256u : clear_code + 2;
 
     MatchState m;
-    m.pw = 0;
-    m.next_code = first_code;
-    m.write_size = fixed ? 12u : cs + 1;
-    m.mask = (1u << m.write_size) - inc;
+    m.t = 0;
+    m.ncs = scr(first_code);
+    m.ws = FIXED ? 12u : cs + 1;
+    m.mask = (1u << m.ws) - inc;
+    m.until = FIXED ? 4096u - first_code : m.mask - first_code + 1u;
     m.ncodes = 0;
-    m.status = SLZW_OK;
-    m.detail = 0;
+    uint32_t status = SLZW_OK, detail = 0;
 
     // ---- packed-window state (warp-uniform) ----
     const uint32_t mis = dst ? (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u) : 0u;
@@ -324,34 +306,34 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, EncWarpSmem<SLOTS
     const uint64_t limit = cap > (~0ull - 7) / 8 ? ~0ull : cap * 8 + 7;
 
     auto push = [&](uint32_t code, uint32_t width) {  // BitWriter::write, io.rs:234-237, 296-300
-        S.codes[m.ncodes++] = (uint16_t)((code & ((1u << width) - 1)) | (width << 12));
+        codes[m.ncodes++] = (uint16_t)(scr(code) | (width << 12));
     };
 
     // Whole warp: bit-pack the buffered codes, flush complete words.
     auto pack_and_flush = [&](uint32_t count) {
         for (uint32_t base = 0; base < count; base += kWarpSize) {
             const uint32_t idx = base + lane;
-            const uint32_t e = idx < count ? S.codes[idx] : 0u;
-            const uint32_t w = e >> 12;
-            const uint32_t code = e & 0xFFFu;
-            uint32_t x = w;
+            const uint32_t e = idx < count ? codes[idx] : 0u;
+            const uint32_t wd = e >> 12;
+            const uint32_t code = unscr(e) & ((1u << wd) - 1u);  // BitWriter masks to the width
+            uint32_t x = wd;
 #pragma unroll
             for (int d = 1; d < kWarpSize; d <<= 1) {
                 const uint32_t y = __shfl_up_sync(kFullMask, x, d);
                 if (lane >= d) x += y;
             }
-            const uint32_t off = qbits + x - w;
+            const uint32_t off = qbits + x - wd;
             const uint32_t total = __shfl_sync(kFullMask, x, kWarpSize - 1);
-            if (w) {
+            if (wd) {
                 const uint32_t wi = off >> 5, sh = off & 31u;
                 if (!big) {
                     const uint64_t v = (uint64_t)code << sh;
-                    atomicOr(&S.outw[wi], (uint32_t)v);
-                    if (v >> 32) atomicOr(&S.outw[wi + 1], (uint32_t)(v >> 32));
+                    atomicOr(&outw[wi], (uint32_t)v);
+                    if (v >> 32) atomicOr(&outw[wi + 1], (uint32_t)(v >> 32));
                 } else {
-                    const uint64_t v = (uint64_t)code << (64 - w - sh);
-                    atomicOr(&S.outw[wi], (uint32_t)(v >> 32));
-                    if ((uint32_t)v) atomicOr(&S.outw[wi + 1], (uint32_t)v);
+                    const uint64_t v = (uint64_t)code << (64 - wd - sh);
+                    atomicOr(&outw[wi], (uint32_t)(v >> 32));
+                    if ((uint32_t)v) atomicOr(&outw[wi + 1], (uint32_t)v);
                 }
             }
             qbits += total;
@@ -360,11 +342,11 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, EncWarpSmem<SLOTS
         __syncwarp();
         const uint32_t cw = qbits >> 5;
         if (dst)
-            for (uint32_t w = lane; w < cw; w += kWarpSize)
-                store_word(dst, mis, cap, wbase + w, S.outw[w], big);
-        const uint32_t carry = S.outw[cw];
+            for (uint32_t k = lane; k < cw; k += kWarpSize)
+                store_word(dst, mis, cap, wbase + k, outw[k], big);
+        const uint32_t carry = outw[cw];
         __syncwarp();
-        for (uint32_t w = lane; w <= cw; w += kWarpSize) S.outw[w] = (w == 0) ? carry : 0u;
+        for (uint32_t k = lane; k <= cw; k += kWarpSize) outw[k] = (k == 0) ? carry : 0u;
         wbase += cw;
         qbits &= 31u;
         __syncwarp();
@@ -372,103 +354,84 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, EncWarpSmem<SLOTS
 
     __syncwarp();
 
-    {   // executed by every lane with identical values (warp-uniform control flow)
-        if (!fixed) push(clear_code, m.write_size);  // encoder.rs:297
-        if (n > 0) {
-            const uint32_t first = __ldg(src);  // encoder.rs:311 / 637: not range-checked
-            m.pw = first << 20;
-            if (!fixed && n > 1 && first >= first_code) {
-                // find_word would index past tree.nodes (encoder.rs:99) unless the second byte
-                // is rejected first (encoder.rs:315-317)
-                const uint32_t k = __ldg(src + 1);
-                if (k > max_code) {
-                    m.status = SLZW_ERR_UNEXPECTED_CODE;
-                    m.detail = k;
-                } else {
-                    m.status = SLZW_ERR_REFERENCE_PANIC;
-                }
+    if (!FIXED) push(clear_code, m.ws);  // encoder.rs:297
+    if (n > 0) {
+        const uint32_t first = __ldg(src);  // encoder.rs:311 / 637: not range-checked
+        m.t = scr(first) << 20;
+        if (!FIXED && n > 1 && first >= first_code) {
+            // find_word would index past tree.nodes (encoder.rs:99) unless the second byte
+            // is rejected first (encoder.rs:315-317)
+            const uint32_t k = __ldg(src + 1);
+            if (k > max_code) {
+                status = SLZW_ERR_UNEXPECTED_CODE;
+                detail = k;
+            } else {
+                status = SLZW_ERR_REFERENCE_PANIC;
             }
         }
     }
     // the leading clear code alone overflows a tiny slot before the first byte is even read
-    if (!fixed && (uint64_t)m.write_size > limit) m.status = SLZW_ERR_IO_WRITE_ZERO;
-    uint32_t status = __shfl_sync(kFullMask, m.status, 0);
+    if (!FIXED && (uint64_t)m.ws > limit) {
+        status = SLZW_ERR_IO_WRITE_ZERO;
+        detail = 0;
+    }
 
     while (status == SLZW_OK && pos < n) {
-        // prefetch the next tile into the other buffer, then wait for the current one
+        // ---- records of this tile; input validation (encoder.rs:315-317) truncates it ----
+        uint32_t bad = 0xFFFFFFFFu;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const uint32_t idx = 4u * (uint32_t)lane + (uint32_t)b - skew;  // wraps before the tile
+            const uint32_t k = (w >> (8 * b)) & 0xFFu;
+            if (idx < tile_len) {
+                rec[idx] = make_uint2(k << 12, tb | (((k * kByteMul) << 2) & kIdxMask4));
+                if (!FIXED && k > max_code && idx < bad) bad = idx;
+            }
+        }
+        // the lookahead of the tile's last byte reads one record past the end: keep its probe
+        // address inside the dictionary
+        if (lane == 0) rec[tile_len] = make_uint2(0u, tb);
+        uint32_t len = tile_len;
+        if (!FIXED && cs < 8) {
+            bad = __reduce_min_sync(kFullMask, bad);
+            if (bad < len) len = bad;
+        }
+        // next tile's words (aligned from here on) in flight during the match loop
         const uint64_t npos = pos + tile_len;
         const uint32_t nlen = (uint32_t)((n - npos) < (uint64_t)TILE ? (n - npos) : TILE);
-        uint32_t nskew = 0;
-        if (nlen) {
-            nskew = stage_tile_async(src + npos, nlen, S.tile[buf ^ 1], lane);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
+        const uint32_t wn = nlen ? load_tile_word(src + npos, 0u, nlen, lane) : 0u;
         __syncwarp();
-        // The guarded loop is only needed when this tile could overflow the slot (upper bound:
-        // 12 bits per byte plus the codes still buffered).
-        const uint64_t pending = (uint64_t)__shfl_sync(kFullMask, m.ncodes, 0) * 12u;
-        const uint64_t used = bits + pending;
-        const bool guard = (limit > used ? limit - used : 0) < 12ull * (TILE + 8);
-        uint32_t i = 0;
-        for (;;) {
-            uint32_t reason = R_TILE_END;
-            {   // every lane runs the match loop redundantly: uniform branches, broadcast loads
-                const uint8_t* t = S.tile[buf] + skew;
-#define SLZW_MATCH(CHK, FIX, GRD, ROOM)                                                    \
-    match_tile<SLOTS, CHK, FIX, GRD>(S.table, S.codes, lane, t, i, tile_len, m, ROOM,   \
-                                     max_code, first_code, clear_code, cs, inc)
-                if (guard) {
-                    // exact room: bits already packed plus the widths of the buffered codes
-                    uint32_t pend = 0;
-                    for (uint32_t c = 0; c < m.ncodes; c++) pend += S.codes[c] >> 12;
-                    const int64_t r = (int64_t)(limit > bits ? limit - bits : 0) - (int64_t)pend;
-                    const int32_t room = (int32_t)(r > 0x3FFFFFFF ? 0x3FFFFFFF : r);
-                    if (fixed)
-                        reason = SLZW_MATCH(false, true, true, room);
-                    else
-                        reason = SLZW_MATCH(true, false, true, room);
-                } else if (fixed) {
-                    reason = SLZW_MATCH(false, true, false, 0);
-                } else if (cs == 8) {
-                    reason = SLZW_MATCH(false, false, false, 0);
-                } else {
-                    reason = SLZW_MATCH(true, false, false, 0);
-                }
-#undef SLZW_MATCH
-            }
-            reason = __shfl_sync(kFullMask, reason, 0);
-            if (reason == R_RESET) {  // tree.reset(), encoder.rs:332
-                for (int j = lane; j < SLOTS / 4; j += kWarpSize)
-                    reinterpret_cast<uint4*>(S.table)[j] = make_uint4(0, 0, 0, 0);
-                __syncwarp();
-                continue;
-            }
-            break;
-        }
-        status = __shfl_sync(kFullMask, m.status, 0);
-        const uint32_t cnt = __shfl_sync(kFullMask, m.ncodes, 0);
-        pack_and_flush(cnt);
+
+        if (len)
+            match_tile<FIXED>(table, tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
+        __syncwarp();
+
+        pack_and_flush(m.ncodes);
         m.ncodes = 0;
+        // The `&mut [u8]` writer fails at the first byte past the slot (io.rs:244 / 307).  Codes
+        // are emitted in input order, so a write failure inside this tile precedes a rejected
+        // byte that ended it.
+        if (bits > limit) {
+            status = SLZW_ERR_IO_WRITE_ZERO;
+        } else if (len < tile_len) {
+            status = SLZW_ERR_UNEXPECTED_CODE;
+            detail = rec[len].x >> 12;
+        }
         pos = npos;
         tile_len = nlen;
-        skew = nskew;
-        buf ^= 1;
+        skew = 0;
+        w = wn;
     }
-    cp_async_wait<0>();
 
     // tail codes (only when the whole input was consumed), then pack whatever is buffered --
     // on an error the codes written before it stay in the output, like the reference's writer
     if (status == SLZW_OK) {
-        if (n > 0) push(m.pw >> 20, m.write_size);  // encoder.rs:339 / 653
-        if (!fixed) push(eoi, m.write_size);        // encoder.rs:303 / 340
+        if (n > 0) codes[m.ncodes++] = (uint16_t)((m.t >> 20) | (m.ws << 12));  // encoder.rs:339 / 653
+        if (!FIXED) push(eoi, m.ws);                                            // encoder.rs:303 / 340
     }
-    {
-        const uint32_t cnt = __shfl_sync(kFullMask, m.ncodes, 0);
-        pack_and_flush(cnt);
-        m.ncodes = 0;
-    }
+    __syncwarp();
+    pack_and_flush(m.ncodes);
+    m.ncodes = 0;
     if (status == SLZW_OK && bits > limit) status = SLZW_ERR_IO_WRITE_ZERO;
     const bool finished = (status == SLZW_OK);  // the encoder reached fill()
 
@@ -480,7 +443,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, EncWarpSmem<SLOTS
         if (dst) {
             // bytes of the last, partial window word
             const int64_t b0 = (int64_t)(wbase * 4) - (int64_t)mis;
-            uint32_t v = S.outw[0];
+            uint32_t v = outw[0];
             if (big) v = __byte_perm(v, 0, 0x0123);
             for (int j = 0; j < 4; j++) {
                 const int64_t b = b0 + j;
@@ -489,78 +452,106 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, EncWarpSmem<SLOTS
         }
         a.out_len[sid] = total;
         a.status[sid] = status;
-        a.detail[sid] = m.detail;
+        a.detail[sid] = detail;
     }
     __syncwarp();
 }
 
-template <int SLOTS, int TILE, int WARPS>
-__global__ void __launch_bounds__(WARPS * kWarpSize, 1) slzw_encode_kernel(const DevBatch a) {
+// Shared-memory layout of the CTA (dynamic shared memory, base address `base` in the shared
+// window): the dictionaries start at the first 16 KB boundary; the per-warp EncMisc blocks fill
+// the gap in front of it and continue behind the last dictionary.
+template <int TILE, int WARPS>
+struct EncLayout {
+    static constexpr uint32_t kTable = kSlots * 4;
+    static constexpr uint32_t kMisc = (uint32_t)((sizeof(EncMisc<TILE>) + 15) & ~size_t(15));
+    __host__ __device__ static uint32_t first_table(uint32_t base) {
+        return (base + kTable - 1) & ~(kTable - 1);
+    }
+    __host__ __device__ static uint32_t misc_in_front(uint32_t base) {
+        const uint32_t k = (first_table(base) - base) / kMisc;
+        return k < (uint32_t)WARPS ? k : (uint32_t)WARPS;
+    }
+    __host__ __device__ static uint32_t misc_addr(uint32_t base, uint32_t warp) {
+        const uint32_t front = misc_in_front(base);
+        return warp < front ? base + warp * kMisc
+                            : first_table(base) + WARPS * kTable + (warp - front) * kMisc;
+    }
+    __host__ __device__ static uint32_t bytes(uint32_t base) {  // dynamic shared memory needed
+        const uint32_t front = misc_in_front(base);
+        return first_table(base) - base + WARPS * kTable + (WARPS - front) * kMisc;
+    }
+};
+
+template <int TILE, int WARPS, bool FIXED>
+__global__ void __launch_bounds__(WARPS * kWarpSize, 1)
+slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    using Smem = EncWarpSmem<SLOTS, TILE>;
-    const int warp = threadIdx.x / kWarpSize;
+    using L = EncLayout<TILE, WARPS>;
+    const uint32_t warp = threadIdx.x / kWarpSize;
     const int lane = threadIdx.x % kWarpSize;
-    Smem& S = reinterpret_cast<Smem*>(smem_raw)[warp];
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    if (L::bytes(base) > dyn_bytes) __trap();  // launch configuration and layout disagree
+    const uint32_t tb = L::first_table(base) + warp * L::kTable;
+    uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw + (tb - base));
+    EncMisc<TILE>& S = *reinterpret_cast<EncMisc<TILE>*>(smem_raw + (L::misc_addr(base, warp) - base));
     for (;;) {
         unsigned long long q = 0;
         if (lane == 0) q = atomicAdd(a.queue, 1ull);
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= a.n) break;
         const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-        encode_stream<SLOTS, TILE>(a, sid, S, lane);
+        encode_stream<TILE, FIXED>(a, sid, table, tb, S, lane);
     }
 }
 
 }  // namespace
 
 // ---- launch configuration ---------------------------------------------------------------------
-// {dictionary slots, input tile, warps per CTA}: 4096 slots = 16 KB per stream (load <= 0.94,
-// wide probing) lets 12-13 streams share one SM's shared memory.
-template <int SLOTS, int TILE, int WARPS>
+// {input tile, warps (= streams) per SM}
+template <int TILE, int WARPS>
 struct EncConfig {
-    static size_t smem() { return sizeof(EncWarpSmem<SLOTS, TILE>) * WARPS; }
+    using L = EncLayout<TILE, WARPS>;
+    // the shared window of a CTA starts with 1 KB reserved by the system; taking the larger of
+    // the two layouts keeps the launch valid should the dynamic region start at 0 instead
+    static uint32_t smem() {
+        const uint32_t a = L::bytes(1024u), b = L::bytes(0u);
+        return a > b ? a : b;
+    }
     static cudaError_t configure() {
-        return cudaFuncSetAttribute(slzw_encode_kernel<SLOTS, TILE, WARPS>,
+        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, WARPS, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, WARPS, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
     }
-    static cudaError_t launch(const DevBatch& a, int grid, cudaStream_t stream) {
-        slzw_encode_kernel<SLOTS, TILE, WARPS><<<grid, WARPS * kWarpSize, smem(), stream>>>(a);
+    static cudaError_t launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
+        const uint64_t ctas = (a.n + WARPS - 1) / WARPS;
+        const int grid = (int)(ctas < (uint64_t)num_sms ? ctas : (uint64_t)num_sms);
+        if (a.p.flavour == SLZW_FLAVOUR_FIXED)
+            slzw_encode_kernel<TILE, WARPS, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+        else
+            slzw_encode_kernel<TILE, WARPS, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         return cudaGetLastError();
     }
 };
 
-using Enc0 = EncConfig<4096, 192, 13>;  // default: measured fastest (profiles/r01_encode_configs.md)
-using Enc1 = EncConfig<4096, 256, 12>;
-using Enc2 = EncConfig<8192, 512, 6>;
-using Enc3 = EncConfig<4096, 256, 8>;
+using Enc0 = EncConfig<128, 12>;
+using Enc1 = EncConfig<96, 13>;
+static_assert(sizeof(EncMisc<128>) <= 2048 && sizeof(EncMisc<96>) <= 1280, "EncMisc grew");
 
 static int g_enc_config = 0;
 
-void encode_select_config(int c) { g_enc_config = (c >= 0 && c <= 3) ? c : 0; }
-int encode_warps_per_cta() {
-    switch (g_enc_config) {
-        case 1: return 12;
-        case 2: return 6;
-        case 3: return 8;
-        default: return 13;
-    }
-}
+void encode_select_config(int c) { g_enc_config = (c == 1) ? 1 : 0; }
+int encode_streams_per_sm() { return g_enc_config == 1 ? 13 : 12; }
 
 cudaError_t encode_configure() {
-    cudaError_t e;
-    if ((e = Enc0::configure()) != cudaSuccess) return e;
-    if ((e = Enc1::configure()) != cudaSuccess) return e;
-    if ((e = Enc2::configure()) != cudaSuccess) return e;
-    return Enc3::configure();
+    cudaError_t e = Enc0::configure();
+    if (e != cudaSuccess) return e;
+    return Enc1::configure();
 }
 
-cudaError_t encode_launch(const DevBatch& a, int grid, cudaStream_t stream) {
-    switch (g_enc_config) {
-        case 1: return Enc1::launch(a, grid, stream);
-        case 2: return Enc2::launch(a, grid, stream);
-        case 3: return Enc3::launch(a, grid, stream);
-        default: return Enc0::launch(a, grid, stream);
-    }
+cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
+    return g_enc_config == 1 ? Enc1::launch(a, num_sms, stream) : Enc0::launch(a, num_sms, stream);
 }
 
 }  // namespace slzw

@@ -17,9 +17,9 @@
 namespace slzw {
 // encode_kernels.cu
 void encode_select_config(int c);
-int encode_warps_per_cta();
+int encode_streams_per_sm();
 cudaError_t encode_configure();
-cudaError_t encode_launch(const DevBatch& a, int grid, cudaStream_t stream);
+cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream);
 // decode_kernels.cu
 size_t decode_exact_smem_bytes();
 int decode_exact_warps_per_cta();
@@ -195,7 +195,7 @@ int run_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, cu
         a.out_off = nullptr;
     }
     if (op == Op::Encode) {
-        CK(encode_launch(a, grid_for(ctx, b->n, encode_warps_per_cta()), stream), "encode launch");
+        CK(encode_launch(a, ctx->num_sms, stream), "encode launch");
     } else {
         CK(decode_exact_launch(a, grid_for(ctx, b->n, decode_exact_warps_per_cta()), stream),
            "decode launch");

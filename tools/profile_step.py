@@ -14,6 +14,7 @@ def main():
     ap.add_argument("--streams", type=int, default=2048)
     ap.add_argument("--passes", type=int, default=2)
     ap.add_argument("--what", default="all", choices=["all", "encode", "decode"])
+    ap.add_argument("--cls", type=int, default=-1, help="keep only streams of entropy class cls (i mod 4)")
     args = ap.parse_args()
     import torch
 
@@ -25,6 +26,12 @@ def main():
     codec = lzw_b200.Codec(0)
     p = tiff_params()
     buf, off = W.tiff_strips(args.streams)
+    if args.cls >= 0:
+        idx = np.arange(args.cls, args.streams, 4)
+        parts = [buf[int(off[i]):int(off[i + 1])] for i in idx]
+        off = np.zeros(len(parts) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([p.size for p in parts])
+        buf = np.concatenate(parts)
     slots = W.encode_slots(off)
     n = off.size - 1
     i64 = lambda a: torch.from_numpy(a.view(np.int64)).to(dev)
