@@ -130,6 +130,11 @@ SLZW_API const char* slzw_last_error(const slzw_ctx* ctx);
 /* kernels launched by this context so far (for benchmark accounting) */
 SLZW_API uint64_t slzw_kernel_launches(const slzw_ctx* ctx);
 SLZW_API uint32_t slzw_version(void);
+/* Diagnostics: the streams of the most recent decode call of this context that the fast decode
+ * kernel handed to the exact-emulation kernel (malformed streams, full output slots, slots larger
+ * than 1 MiB; see decode_kernels.cu).  Synchronises the device.  Returns their number and
+ * copies up to `cap` stream ids into `ids` (may be NULL). */
+SLZW_API uint64_t slzw_last_deferred(slzw_ctx* ctx, uint32_t* ids, uint64_t cap);
 
 /* ---- batched entry points (the hot path; new relative to the reference) ----------------- */
 /* Device-resident batch, asynchronous on `cuda_stream` (a cudaStream_t, may be NULL).

@@ -49,6 +49,12 @@ class Codec:
     def kernel_launches(self) -> int:
         return int(self._lib.slzw_kernel_launches(self._h))
 
+    def last_deferred(self, cap: int = 1024) -> np.ndarray:
+        """Ids of the streams the last decode call handed to the exact-emulation kernel."""
+        ids = np.zeros(max(cap, 1), dtype=np.uint32)
+        n = int(self._lib.slzw_last_deferred(self._h, ids.ctypes.data, cap))
+        return ids[: min(n, cap)] if n <= cap else np.concatenate([ids[:cap], np.full(n - cap, 0xFFFFFFFF, np.uint32)])
+
     def encode_bound(self, params: Params, n: int) -> int:
         return int(self._lib.slzw_encode_bound(C.byref(params), n))
 

@@ -1,8 +1,28 @@
 // decode_kernels.cu -- batched LZW decoder for sm_100a.
 //
-// slzw_decode_exact_kernel: one warp per stream, persistent CTAs, streams handed out through
-// the scheduler's work queue.  It reproduces VariableDecoder::inner_decode (decoder.rs:174-290)
-// and FixedDecoder::inner_decode (decoder.rs:553-642) state for state -- prefix/suffix/length
+// Two kernels, both one warp per stream, persistent CTAs, streams handed out through the
+// scheduler's work queue:
+//
+// slzw_decode_fast_kernel -- the throughput path.  The reference's prefix-chain walk
+// (decoder.rs:251-267) is replaced by an (output offset, length) table: entry n is the word that
+// was written for the previous code plus the first byte of the current word, and those bytes are
+// contiguous in the stream's own output, so an entry is just (offset of the previous word,
+// its length + 1) (equivalent to decoder.rs:272-275).  The warp decodes up to 32 codes per
+// step, one per lane: parallel bit extraction (io.rs:43-55 / 113-128; all codes of a step have
+// the same width because steps end where the width changes, decoder.rs:277-280), table lookup,
+// resolution of codes that name entries created inside the same step (including the KwKwK case,
+// decoder.rs:244-250), a prefix sum of the word lengths, then a byte-parallel gather: every
+// output byte of the step finds its word through a bit mask of word starts, follows source
+// pointers that still point into the step itself, loads its byte from the stream's already
+// decoded output and stores it, coalesced.  Anything that is not the plain, successful case --
+// a code beyond the table, a missing clear code, input that ends before the end-of-information
+// code, a first code after a clear that is not a root (decoder.rs:230-236), a full output slot,
+// a word longer than the reference's stack, a slot larger than 1 MiB (offsets are 20 bits) --
+// makes the kernel DEFER the stream: it is appended to a retry list and decoded again, from
+// scratch, by the exact kernel.
+//
+// slzw_decode_exact_kernel -- reproduces VariableDecoder::inner_decode (decoder.rs:174-290) and
+// FixedDecoder::inner_decode (decoder.rs:553-642) state for state -- prefix/suffix/length
 // tables and the word stack live in shared memory -- so that every observable result matches
 // the reference, including the ones that depend on stale table contents (tables are not
 // cleared on a clear code, decoder.rs:222-227; the first code after a clear is not
@@ -275,13 +295,343 @@ __global__ void __launch_bounds__(WARPS * kWarpSize, 1) slzw_decode_exact_kernel
     const int warp = threadIdx.x / kWarpSize;
     const int lane = threadIdx.x % kWarpSize;
     Smem& S = reinterpret_cast<Smem*>(smem_raw)[warp];
+    // n_dev != nullptr: the streams are the ones the fast kernel deferred (count on the device)
+    const uint64_t count = a.n_dev ? (uint64_t)*reinterpret_cast<const volatile uint32_t*>(a.n_dev) : a.n;
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(a.queue, 1ull);
+        q = __shfl_sync(kFullMask, q, 0);
+        if (q >= count) break;
+        const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
+        decode_stream_exact<TILE, OUTB>(a, sid, S, lane);
+    }
+}
+
+
+// ---- fast kernel ---------------------------------------------------------------------------------
+constexpr int kFastWin = 1024;   // output bytes one step may produce (32 mask words)
+constexpr int kFastTile = 512;   // compressed bytes staged per tile
+constexpr uint32_t kLit = 0x80000000u;
+constexpr uint32_t kFastMaxOut = 1u << 20;  // table entries hold 20-bit output offsets
+
+struct FastWarpSmem {
+    uint32_t table[kMaxTable];           // entry = output offset << 12 | length
+    uint32_t bits[kFastWin / 32];        // word starts of the current step
+    __align__(16) uint8_t tile[kFastTile + 32];
+};
+
+// Returns false when the stream has to be decoded by the exact kernel.
+__device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem& S, int lane) {
+    const uint64_t in_begin = a.in_off[sid];
+    const uint64_t n = a.in_off[sid + 1] - in_begin;
+    const uint8_t* src = a.in + in_begin;
+    uint8_t* dst = nullptr;
+    uint64_t cap = ~0ull;
+    if (a.out != nullptr) {
+        const uint64_t ob = a.out_off[sid];
+        dst = a.out + ob;
+        cap = a.out_off[sid + 1] - ob;
+        if (cap > kFastMaxOut) return false;
+    }
+    const bool fixed = a.p.flavour == SLZW_FLAVOUR_FIXED;
+    const bool big = a.p.big_endian != 0;
+    const uint32_t inc = (!fixed && a.p.tiff_early_change) ? 1u : 0u;
+    const uint32_t cs = fixed ? 8u : (a.code_size ? a.code_size[sid] : a.p.code_size);
+    if (!fixed && (cs < 2 || cs > 8)) {  // decoder.rs:180-182
+        if (lane == 0) {
+            a.out_len[sid] = 0;
+            a.status[sid] = SLZW_ERR_CODE_SIZE;
+            a.detail[sid] = cs;
+        }
+        return true;
+    }
+
+    const uint32_t roots = fixed ? 256u : (1u << cs);  // codes below are single bytes
+    const uint32_t clear_code = roots, eoi = roots + 1;  // variable flavour only
+    const uint32_t first_index = fixed ? 256u : roots + 2;
+    uint32_t w = fixed ? 12u : cs + 1;       // read_size, decoder.rs:208
+    uint32_t mask = (1u << w) - inc;         // decoder.rs:211
+    uint32_t nidx = first_index;             // next_index
+    bool hp = false;                         // previous_code.is_some()
+    uint32_t prev_off = 0, prev_len = 0;     // the previous word, in the output
+    uint64_t bitpos = 0;
+    const uint64_t total_bits = n * 8;
+    uint32_t produced = 0;                   // bytes written (<= 2^20 when dst != nullptr)
+    uint64_t produced64 = 0;                 // size-only passes are not bounded
+    uint32_t status = SLZW_OK, detail = 0;
+    uint64_t tile_pos = 0;
+    uint32_t tile_len = 0, skew = 0;         // S.tile[skew + j] = src[tile_pos + j], j < tile_len
+    const uint32_t lanemask_le = 0xFFFFFFFFu >> (31 - lane);
+
+    for (;;) {
+        // ---- how many codes this step may read at the current width ----
+        const uint64_t avail64 = (total_bits - bitpos) / w;
+        if (avail64 == 0) {
+            // fixed: the iterator ends, decoder.rs:585 (leftover bits ignored, io.rs:62-64);
+            // variable: read_exact fails, Io(UnexpectedEof), decoder.rs:220 -- the bytes written
+            // so far stay (this is how SURVEY.md F1 streams end)
+            if (!fixed) status = SLZW_ERR_IO_UNEXPECTED_EOF;
+            break;
+        }
+        uint32_t bmax = avail64 < 32 ? (uint32_t)avail64 : 32u;
+        const uint32_t adj = hp ? 0u : 1u;   // the first code after a clear creates no entry
+        if (!(fixed && nidx >= (uint32_t)kMaxTable)) {
+            const uint32_t room = (w < 12u ? mask : (uint32_t)kMaxTable) - nidx + adj;
+            if (room < bmax) bmax = room;
+        }
+        const uint32_t bn = bmax ? bmax : 1u;  // bmax == 0: table full, a control code must follow
+
+        // ---- stage the compressed bytes of the step ----
+        {
+            const uint64_t first = bitpos >> 3;
+            const uint64_t last = (bitpos + 32u * 12u + 7u) >> 3;  // exclusive upper bound
+            if (first < tile_pos || (last > tile_pos + tile_len && tile_pos + tile_len < n)) {
+                tile_pos = first;
+                tile_len = (uint32_t)((n - tile_pos) < (uint64_t)kFastTile ? (n - tile_pos) : kFastTile);
+                __syncwarp();
+                skew = stage_tile(src + tile_pos, tile_len, S.tile, lane);
+                __syncwarp();
+            }
+        }
+
+        // ---- one code per lane (io.rs:43-55 / 113-128) ----
+        uint32_t c;
+        {
+            const uint64_t bit = bitpos + (uint64_t)lane * w;
+            const uint32_t ba = skew + (uint32_t)((bit >> 3) - tile_pos);
+            const uint32_t* tw = reinterpret_cast<const uint32_t*>(S.tile);
+            uint32_t v = 0;
+            if ((uint32_t)lane < bn) v = __funnelshift_r(tw[ba >> 2], tw[(ba >> 2) + 1], (ba & 3u) * 8u);
+            const uint32_t sh = (uint32_t)bit & 7u;
+            if (!big) c = (v >> sh) & ((1u << w) - 1u);
+            else c = (__byte_perm(v, 0, 0x0123) >> (32u - w - sh)) & ((1u << w) - 1u);
+        }
+        // control codes end the step (decoder.rs:222-229)
+        uint32_t b = bn;
+        uint32_t ctrl = 0xFFFFFFFFu;  // the control code that ends this step, if any
+        if (!fixed) {
+            const uint32_t cm = __ballot_sync(kFullMask, (uint32_t)lane < bn && (c == clear_code || c == eoi));
+            if (cm) {
+                b = (uint32_t)__ffs(cm) - 1u;
+                ctrl = __shfl_sync(kFullMask, c, b);
+            }
+        }
+        if (bmax == 0 && ctrl == 0xFFFFFFFFu) return false;  // MissingClearCode, decoder.rs:281-283
+
+        if (b > 0) {
+            // ---- classify (decoder.rs:230-268) ----
+            // the entry index this lane's code is compared with (next_index at that moment)
+            const uint32_t ni = nidx + (uint32_t)lane - adj;
+            // UnexpectedCode (decoder.rs:241-243): the words before it are still written
+            {
+                const uint32_t um = __ballot_sync(kFullMask, (uint32_t)lane < b && (uint32_t)lane >= adj &&
+                                                                 c >= roots && c > ni);
+                if (um) {
+                    const uint32_t f = (uint32_t)__ffs(um) - 1u;
+                    status = SLZW_ERR_UNEXPECTED_CODE;
+                    detail = __shfl_sync(kFullMask, c, (int)f);
+                    b = f;
+                    ctrl = 0xFFFFFFFFu;
+                }
+            }
+        }
+        if (b > 0) {
+            const bool act = (uint32_t)lane < b;
+            bool bad = false;
+            uint32_t len = 0, srci = 0;
+            int qd = -2;  // >= -1: the word extends the word of step code qd (-1 = previous step)
+            if (act) {
+                if (c < roots) {
+                    len = 1;
+                    srci = kLit | c;
+                } else if (!hp && lane == 0) {
+                    bad = true;  // first code is not a root: stale-table semantics, decoder.rs:230-236
+                } else if (c < nidx) {
+                    const uint32_t e = S.table[c];
+                    len = e & 0xFFFu;
+                    srci = e >> 12;
+                } else {  // c <= ni: an entry created inside this step, or the one being created
+                    qd = (int)(c - nidx + adj) - 1;
+                }
+            }
+            if (__any_sync(kFullMask, bad)) return false;
+            // ---- lengths of words that extend a word of this step ----
+            bool known = qd < 0;
+            if (qd == -1) len = prev_len + 1u;
+            for (;;) {
+                if (!__any_sync(kFullMask, !known)) break;
+                const int from = qd > 0 ? qd : 0;
+                const uint32_t lk = __shfl_sync(kFullMask, len, from);
+                const bool kk = __shfl_sync(kFullMask, (int)known, from) != 0;
+                if (!known && kk) {
+                    len = lk + 1u;
+                    known = true;
+                }
+            }
+            // a word longer than the reference's stack panics there (decoder.rs:247, 262, 270)
+            if (__any_sync(kFullMask, act && len > (uint32_t)kMaxStack)) return false;
+            // ---- output positions ----
+            uint32_t incl = act ? len : 0u;
+#pragma unroll
+            for (int d = 1; d < kWarpSize; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(kFullMask, incl, d);
+                if (lane >= d) incl += y;
+            }
+            uint32_t total = __shfl_sync(kFullMask, incl, (int)b - 1);
+            if (total > (uint32_t)kFastWin && b > 1) {
+                // keep the codes whose words fit the window (at least one)
+                const uint32_t fit = __ballot_sync(kFullMask, act && incl <= (uint32_t)kFastWin);
+                uint32_t nb = (uint32_t)__popc(fit);
+                if (nb == 0) nb = 1;
+                b = nb;
+                ctrl = 0xFFFFFFFFu;
+                status = SLZW_OK;  // a code beyond the table, if any, is met again in a later step
+                detail = 0;
+                total = __shfl_sync(kFullMask, incl, (int)b - 1);
+            }
+            const bool act2 = (uint32_t)lane < b;
+            const uint32_t pos = incl - len;  // relative to `produced`
+            // Io(WriteZero): the `&mut [u8]` writer takes the bytes that still fit, then fails
+            // (decoder.rs:231, 270); nothing after that is observable
+            const uint32_t nr_set = (total + 31u) >> 5;  // mask words that get word-start bits
+            if (dst && (uint64_t)produced + total > cap) {
+                status = SLZW_ERR_IO_WRITE_ZERO;
+                detail = 0;
+                total = (uint32_t)(cap - produced);
+            }
+            {
+                const uint32_t pq = __shfl_sync(kFullMask, pos, qd > 0 ? qd : 0);
+                if (qd >= 0) srci = produced + pq;
+                else if (qd == -1) srci = prev_off;
+            }
+            // ---- new entries (decoder.rs:272-276 / 630-634) ----
+            {
+                uint32_t poff = produced + __shfl_up_sync(kFullMask, pos, 1);
+                uint32_t plen = __shfl_up_sync(kFullMask, len, 1);
+                if (lane == 0) {
+                    poff = prev_off;
+                    plen = prev_len;
+                }
+                const uint32_t idx = nidx + (uint32_t)lane - adj;
+                if (act2 && (uint32_t)lane >= adj && idx < (uint32_t)kMaxTable)
+                    S.table[idx] = (poff << 12) | ((plen + 1u) & 0xFFFu);
+            }
+            // ---- copy ----
+            if (dst) {
+                if (nr_set > (uint32_t)(kFastWin / 32)) {
+                    // a single long word (b == 1): periodic copy, the source may run into the word
+                    const uint32_t so = __shfl_sync(kFullMask, srci, 0);
+                    const uint32_t wl = total;
+                    if (so & kLit) {
+                        if (lane == 0) dst[produced] = (uint8_t)so;
+                    } else {
+                        const uint32_t dist = produced - so;  // > 0; the word repeats with this period
+                        for (uint32_t i = lane; i < wl; i += kWarpSize)
+                            dst[produced + i] = dst[so + i % dist];
+                    }
+                } else {
+                    if (act2) atomicOr(&S.bits[pos >> 5], 1u << (pos & 31u));
+                    __syncwarp();
+                    const uint32_t nr = (total + 31u) >> 5;  // rounds that write bytes
+                    const uint32_t wbits = (uint32_t)lane < nr_set ? S.bits[lane] : 0u;
+                    uint32_t cnt = (uint32_t)__popc(wbits);  // -> exclusive prefix count of word starts
+                    {
+                        uint32_t x = cnt;
+#pragma unroll
+                        for (int d = 1; d < kWarpSize; d <<= 1) {
+                            const uint32_t y = __shfl_up_sync(kFullMask, x, d);
+                            if (lane >= d) x += y;
+                        }
+                        cnt = x - cnt;
+                    }
+                    for (uint32_t r = 0; r < nr; r++) {
+                        const uint32_t m = __shfl_sync(kFullMask, wbits, (int)r);
+                        const uint32_t cb = __shfl_sync(kFullMask, cnt, (int)r);
+                        const uint32_t ob = 32u * r + (uint32_t)lane;  // output byte of this lane
+                        const bool on = ob < total;
+                        int own = (int)(cb + (uint32_t)__popc(m & lanemask_le)) - 1;
+                        if (!on) own = 0;
+                        uint32_t sp = __shfl_sync(kFullMask, srci, own);
+                        uint32_t i = ob - __shfl_sync(kFullMask, pos, own);
+                        // sources that lie inside this step: follow them (they strictly decrease)
+                        for (;;) {
+                            const bool inb = on && !(sp & kLit) && sp + i >= produced;
+                            if (!__any_sync(kFullMask, inb)) break;
+                            const uint32_t rel = inb ? sp + i - produced : 0u;
+                            const uint32_t m2 = __shfl_sync(kFullMask, wbits, (int)(rel >> 5));
+                            const uint32_t c2 = __shfl_sync(kFullMask, cnt, (int)(rel >> 5));
+                            const int own2 = (int)(c2 + (uint32_t)__popc(m2 & (0xFFFFFFFFu >> (31u - (rel & 31u))))) - 1;
+                            const uint32_t s2 = __shfl_sync(kFullMask, srci, own2);
+                            const uint32_t p2 = __shfl_sync(kFullMask, pos, own2);
+                            if (inb) {
+                                sp = s2;
+                                i = rel - p2;
+                            }
+                        }
+                        if (on) dst[produced + ob] = (sp & kLit) ? (uint8_t)sp : dst[sp + i];
+                    }
+                    if ((uint32_t)lane < nr_set) S.bits[lane] = 0u;
+                }
+            }
+            // ---- state (decoder.rs:272-284) ----
+            prev_off = produced + __shfl_sync(kFullMask, pos, (int)b - 1);
+            prev_len = __shfl_sync(kFullMask, len, (int)b - 1);
+            produced += total;
+            produced64 += total;
+            bitpos += (uint64_t)b * w;  // all codes of the step were read at the width before a bump
+            if (!(fixed && nidx >= (uint32_t)kMaxTable)) {
+                nidx += b - adj;
+                if (!fixed && nidx == mask && w < 12u) {  // decoder.rs:277-280
+                    w++;
+                    mask = (1u << w) - inc;
+                }
+            }
+            hp = true;
+            __syncwarp();  // the step's stores are visible to the loads of later steps
+        }
+        if (status != SLZW_OK) break;
+        if (ctrl != 0xFFFFFFFFu) {
+            bitpos += w;
+            if (ctrl == eoi) break;  // decoder.rs:228-229, trailing input is ignored
+            // decoder.rs:222-227: the tables themselves are left as they are
+            w = cs + 1;
+            mask = (1u << w) - inc;
+            nidx = first_index;
+            hp = false;
+        }
+    }
+
+    if (lane == 0) {
+        a.out_len[sid] = dst ? (uint64_t)produced : produced64;
+        a.status[sid] = status;
+        a.detail[sid] = detail;
+    }
+    __syncwarp();
+    return true;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * kWarpSize, 1) slzw_decode_fast_kernel(const DevBatch a) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x / kWarpSize;
+    const int lane = threadIdx.x % kWarpSize;
+    FastWarpSmem& S = reinterpret_cast<FastWarpSmem*>(smem_raw)[warp];
+    for (int i = lane; i < kFastWin / 32; i += kWarpSize) S.bits[i] = 0u;
+    __syncwarp();
     for (;;) {
         unsigned long long q = 0;
         if (lane == 0) q = atomicAdd(a.queue, 1ull);
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= a.n) break;
         const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-        decode_stream_exact<TILE, OUTB>(a, sid, S, lane);
+        const bool done = decode_stream_fast(a, sid, S, lane);
+        __syncwarp();
+        if (!done) {
+            // a deferred stream may have left word-start bits behind
+            for (int i = lane; i < kFastWin / 32; i += kWarpSize) S.bits[i] = 0u;
+            if (lane == 0) a.retry_ids[atomicAdd(a.retry, 1u)] = sid;
+            __syncwarp();
+        }
     }
 }
 
@@ -303,6 +653,24 @@ cudaError_t decode_exact_configure() {
 cudaError_t decode_exact_launch(const DevBatch& a, int grid, cudaStream_t stream) {
     slzw_decode_exact_kernel<kDecTile, kDecOutB, kDecWarps>
         <<<grid, kDecWarps * kWarpSize, decode_exact_smem_bytes(), stream>>>(a);
+    return cudaGetLastError();
+}
+
+
+constexpr int kFastWarps = 13;
+
+size_t decode_fast_smem_bytes() { return sizeof(FastWarpSmem) * kFastWarps; }
+int decode_fast_warps_per_cta() { return kFastWarps; }
+
+cudaError_t decode_fast_configure() {
+    return cudaFuncSetAttribute(slzw_decode_fast_kernel<kFastWarps>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)decode_fast_smem_bytes());
+}
+
+cudaError_t decode_fast_launch(const DevBatch& a, int grid, cudaStream_t stream) {
+    slzw_decode_fast_kernel<kFastWarps>
+        <<<grid, kFastWarps * kWarpSize, decode_fast_smem_bytes(), stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -25,6 +25,10 @@ size_t decode_exact_smem_bytes();
 int decode_exact_warps_per_cta();
 cudaError_t decode_exact_configure();
 cudaError_t decode_exact_launch(const DevBatch& a, int grid, cudaStream_t stream);
+size_t decode_fast_smem_bytes();
+int decode_fast_warps_per_cta();
+cudaError_t decode_fast_configure();
+cudaError_t decode_fast_launch(const DevBatch& a, int grid, cudaStream_t stream);
 // sched_kernels.cu
 int sched_size_classes();
 cudaError_t sched_build_order(const uint64_t* off, uint64_t n, uint32_t* hist, uint32_t* order,
@@ -65,14 +69,16 @@ struct DevBuf {
 
 // Scheduler scratch for one in-flight batch.  Reuse on another CUDA stream waits for `done`.
 struct Workspace {
-    DevBuf queue;  // one unsigned long long
+    DevBuf queue;  // kQueueWords x unsigned long long: [0] work queue, [1] retry queue, [2] retry count
     DevBuf hist;   // size classes
     DevBuf order;  // n u32
+    DevBuf retry;  // n u32: streams the fast decoder deferred
     cudaEvent_t done = nullptr;
     bool used = false;
 };
 
 constexpr int kWorkspaces = 4;
+constexpr size_t kQueueWords = 4;
 
 }  // namespace
 
@@ -85,6 +91,7 @@ struct slzw_ctx {
     DevBuf d_in, d_out, d_in_off, d_out_off, d_out_len, d_status, d_detail, d_cs, d_dense, d_dense_off;
     cudaStream_t stream = nullptr;  // host-path stream
     uint64_t launches = 0;
+    int last_decode_ws = -1;  // workspace of the most recent decode call
     char err[256] = {0};
     std::mutex mu;
 };
@@ -127,10 +134,12 @@ int prepare(slzw_ctx* ctx, const uint64_t* d_in_off, uint64_t n, cudaStream_t st
     ctx->ws_next = (ctx->ws_next + 1) % kWorkspaces;
     if (!w.done) CK(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming), "cudaEventCreate");
     if (w.used) CK(cudaStreamWaitEvent(stream, w.done, 0), "cudaStreamWaitEvent");
-    CK(w.queue.reserve(sizeof(unsigned long long)), "cudaMalloc(queue)");
+    CK(w.queue.reserve(sizeof(unsigned long long) * kQueueWords), "cudaMalloc(queue)");
+    CK(w.retry.reserve(sizeof(uint32_t) * n), "cudaMalloc(retry)");
     CK(w.hist.reserve(sizeof(uint32_t) * sched_size_classes()), "cudaMalloc(hist)");
     CK(w.order.reserve(sizeof(uint32_t) * n), "cudaMalloc(order)");
-    CK(cudaMemsetAsync(w.queue.p, 0, sizeof(unsigned long long), stream), "cudaMemsetAsync(queue)");
+    CK(cudaMemsetAsync(w.queue.p, 0, sizeof(unsigned long long) * kQueueWords, stream),
+       "cudaMemsetAsync(queue)");
     CK(sched_build_order(d_in_off, n, (uint32_t*)w.hist.p, (uint32_t*)w.order.p, ctx->num_sms,
                          stream),
        "scheduler launch");
@@ -158,6 +167,9 @@ DevBatch make_dev_batch(const slzw_params* params, const slzw_batch* b, const Wo
     a.n = b->n;
     a.order = (const uint32_t*)w->order.p;
     a.queue = (unsigned long long*)w->queue.p;
+    a.retry = (uint32_t*)((unsigned long long*)w->queue.p + 2);
+    a.retry_ids = (uint32_t*)w->retry.p;
+    a.n_dev = nullptr;
     a.p = *params;
     return a;
 }
@@ -197,6 +209,18 @@ int run_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, cu
     if (op == Op::Encode) {
         CK(encode_launch(a, ctx->num_sms, stream), "encode launch");
     } else {
+        // fast kernel over the whole batch, then the exact kernel over whatever it deferred
+        // (the count lives on the device: the second launch is unconditional and usually idle)
+        ctx->last_decode_ws = (int)(w - ctx->ws);
+        const bool exact_only = getenv("SLZW_DECODE_EXACT") != nullptr;  // debugging knob
+        if (!exact_only) {
+            CK(decode_fast_launch(a, grid_for(ctx, b->n, decode_fast_warps_per_cta()), stream),
+               "fast decode launch");
+            ctx->launches += 1;
+            a.order = a.retry_ids;
+            a.n_dev = a.retry;
+            a.queue = (unsigned long long*)w->queue.p + 1;
+        }
         CK(decode_exact_launch(a, grid_for(ctx, b->n, decode_exact_warps_per_cta()), stream),
            "decode launch");
     }
@@ -398,6 +422,7 @@ int slzw_create(int device, slzw_ctx** out) {
     if (const char* e = getenv("SLZW_ENC_CONFIG")) encode_select_config(atoi(e));  // tuning knob
     DeviceGuard guard(device);
     if (!guard.ok || encode_configure() != cudaSuccess || decode_exact_configure() != cudaSuccess ||
+        decode_fast_configure() != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete ctx;
         return SLZW_RC_CUDA;
@@ -415,6 +440,7 @@ void slzw_destroy(slzw_ctx* ctx) {
             w.queue.release();
             w.hist.release();
             w.order.release();
+            w.retry.release();
             if (w.done) cudaEventDestroy(w.done);
         }
         for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_in_off, &ctx->d_out_off, &ctx->d_out_len,
@@ -427,6 +453,22 @@ void slzw_destroy(slzw_ctx* ctx) {
 
 const char* slzw_last_error(const slzw_ctx* ctx) { return ctx ? ctx->err : "null context"; }
 uint64_t slzw_kernel_launches(const slzw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t slzw_last_deferred(slzw_ctx* ctx, uint32_t* ids, uint64_t cap) {
+    if (!ctx || ctx->last_decode_ws < 0) return 0;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok || cudaDeviceSynchronize() != cudaSuccess) return 0;
+    const Workspace& w = ctx->ws[ctx->last_decode_ws];
+    uint32_t count = 0;
+    if (cudaMemcpy(&count, (const unsigned long long*)w.queue.p + 2, sizeof count,
+                   cudaMemcpyDeviceToHost) != cudaSuccess)
+        return 0;
+    const uint64_t m = count < cap ? count : cap;
+    if (ids && m && cudaMemcpy(ids, w.retry.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return 0;
+    return count;
+}
 
 int slzw_encode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
                              void* cuda_stream) {

@@ -23,7 +23,9 @@ struct DevBatch {
     uint64_t n;
     const uint32_t* order;          // stream ids in processing order (largest first) or nullptr
     unsigned long long* queue;      // work-queue head, zeroed before the launch
-    uint32_t* retry;                // decode: number of streams deferred to the exact kernel
+    uint32_t* retry;                // fast decode: number of streams deferred to the exact kernel
+    uint32_t* retry_ids;            // fast decode: their ids
+    const uint32_t* n_dev;          // exact decode of deferred streams: stream count on the device
     slzw_params p;
 };
 

@@ -61,6 +61,10 @@ def main():
               f"decode_ms={ev[2].elapsed_time(ev[3]):.3f}")
     if args.what != "encode":
         print("round trip equal:", bool(torch.equal(t_dec, t_in)))
+        d = codec.last_deferred()
+        st = t_st.cpu().numpy()
+        ln = t_len.cpu().numpy()
+        print("deferred:", d.size, [(int(i), int(i) % 4, int(off[i + 1] - off[i]), int(ln[i]), int(st[i])) for i in d[:16]])
     codec.close()
 
 
