@@ -111,6 +111,20 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def measured_traffic(kernel: str, n_streams: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed
+    `ncu --set full` capture of this same workload (profiles/r01_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(kernel)
+        if e and int(e.get("streams", -1)) == int(n_streams):
+            return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"])
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -149,10 +163,16 @@ def cpu_baseline(buf, off, sample_streams, threads):
     sub = buf[int(off[0]):int(off[n])]
     te, td = cpu_pass(sub, sub_off, threads)
     nbytes = int(sub_off[-1])
+    # single-threaded figure on a smaller sample (the north star asks for both)
+    m = min(256, n)
+    t1e, t1d = cpu_pass(buf[int(off[0]):int(off[m])], off[: m + 1] - off[0], 1)
+    b1 = int(off[m] - off[0])
     return {
         "value": nbytes / (te + td) / 1e9,
         "unit": UNIT,
         "cores": threads,
+        "single_thread": {"value": b1 / (t1e + t1d) / 1e9, "encode_gbs": b1 / t1e / 1e9,
+                          "decode_gbs": b1 / t1d / 1e9, "sample_streams": m},
         "kind": "port",
         "sample": f"first {n} strips of the workload ({nbytes} uncompressed bytes), oracle/slzw_oracle.c "
                   f"(C restatement of salzweg; the Rust crate cannot be built here), one stream per task "
@@ -306,6 +326,7 @@ def run_ours(args):
         "round_trip_bytes_equal": round_trip_bytes_ok,
         "self_inconsistent_streams(F1)": int((dec_st != 0).sum()),
         "compressed_bytes": comp_total,
+        "streams_deferred_to_exact_decoder": int(codec.last_deferred().size),
     }
     # oracle check of a sample (bytes, sizes, statuses), rank 0 only
     if rank == 0:
@@ -359,6 +380,7 @@ def run_ours(args):
         kernels = {
             "encode": {"ms": enc_ms, "algorithmic_bytes": total + comp},
             "compact": {"ms": cmp_ms, "algorithmic_bytes": 2 * comp},
+            # scheduler + fast kernel + exact kernel over the deferred streams
             "decode": {"ms": dec_ms, "algorithmic_bytes": total + comp},
         }
         for k in kernels.values():
@@ -374,7 +396,8 @@ def run_ours(args):
             "decode_gbs": world * total / (dec_ms * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": f"slzw_{dom}_kernel", "achieved": kernels[dom]["achieved_gbs"],
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "frac": kernels[dom]["frac_of_peak"], "traffic": None,
+                         "frac": kernels[dom]["frac_of_peak"],
+                         "traffic": measured_traffic(f"slzw_{dom}_kernel", n),
                          "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
                          "launch_ms": kernels[dom]["ms"], "frac_of_nominal_8000": kernels[dom]["achieved_gbs"] / 8000.0},
             "kernels": kernels,

@@ -33,6 +33,13 @@ namespace slzw {
 
 namespace {
 
+// Wide handling of miss runs (see match_tile).  Exact, but measured slower on the B200 with linear
+// probing at a load factor of up to 0.94: the longest private probe sequence of the 32 lanes sets
+// the pace (66 slots on average for random bytes), 21.2 ms vs 15.9 ms for 151 MB of random
+// strips and 31.1 ms vs 14.9 ms for photo-like strips (profiles/r01_encode_notes.md).  Kept
+// behind this switch for the next round (bounded probing / double hashing).
+constexpr bool kWideMissRuns = false;
+
 constexpr int kSlots = 4096;
 constexpr uint32_t kIdxMask4 = (uint32_t)(kSlots - 1) << 2;  // byte offset of a slot
 constexpr uint32_t kScr = 0x9E5u;     // code -> code' = code * kScr mod 4096 (odd => bijection)
@@ -131,9 +138,19 @@ __device__ __forceinline__ void clear_table(uint32_t* table, int lane) {
 
 // The match loop of encoder.rs:313-337 / 639-651 over the `len` byte records of one tile.
 // rec[i] = {byte << 12, table base | hash contribution of the byte as a slot byte offset}.
-// Executed by every lane with identical values.  The loop never leaves the tile early: input
-// validation truncates the tile beforehand and the capacity check happens per tile (see
-// encode_stream).
+// The loop never leaves the tile early: input validation truncates the tile beforehand and the
+// capacity check happens per tile (see encode_stream).
+//
+// Two modes, both exact:
+//   * scalar: every lane executes the same dependent chain, one probe per byte, with the probe
+//     of byte i+1 issued speculatively before byte i's comparison resolves (runs of hits);
+//   * wide: after two consecutive misses the current prefix is a single byte, and as long as the
+//     misses go on so is every following prefix -- the keys (byte i-1, byte i) do not depend on
+//     the chain.  Lane j then looks up the key of byte i+j on its own (private linear probing).
+//     Sequentially, byte i+j is a miss that inserts into the empty slot lane j found iff every
+//     earlier lane is a miss too and none of them claimed the same slot (an earlier insert can
+//     only change lane j's lookup by filling exactly that slot, which also covers equal keys).
+//     The warp commits the longest such prefix of lanes at once: codes, inserts, counters.
 template <bool FIXED>
 __device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const uint32_t tb,
                                            const uint2* __restrict__ rec,
@@ -148,15 +165,37 @@ __device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const u
     uint32_t mask = m.mask;
     uint32_t until = m.until;
     uint32_t cp = m.ncodes;
+    uint32_t lastmiss = 0xFFFFFFF0u;  // tile index of the most recent miss
+    uint32_t i = 0;
+    uint2 r0;
+    uint32_t a, s;
 
-    uint2 r0 = rec[0];
-    uint32_t a = (t >> 18) ^ r0.y;  // home slot of (prefix, byte 0); t >> 18 == prefix' << 2
-    uint32_t s = tbl_ld(a);
+    // new index == mask (encoder.rs:326): width bump or clear + dictionary restart
+#define SLZW_BUMP()                                                                             \
+    {                                                                                           \
+        if (ws < 12u) { /* encoder.rs:327-328 */                                                \
+            ws++;                                                                               \
+            wtag = ws << 12;                                                                    \
+            const uint32_t nm = (1u << ws) - inc;                                               \
+            until = nm - mask;                                                                  \
+            mask = nm;                                                                          \
+        } else { /* encoder.rs:329-333: clear at 12 bits, dictionary restarts */                \
+            codes[cp++] = (uint16_t)(scr(clear_code) | (12u << 12));                            \
+            ws = cs + 1u;                                                                       \
+            wtag = ws << 12;                                                                    \
+            mask = (1u << ws) - inc;                                                            \
+            until = mask - first_code + 1u;                                                     \
+            ncs = scr(first_code);                                                              \
+            __syncwarp();                                                                       \
+            clear_table(table, lane);                                                           \
+            __syncwarp();                                                                       \
+        }                                                                                       \
+    }
 
-    // One byte of encoder.rs:313-337.  RC = record of this byte, RN = record of the next byte
-    // (anything addressable when this is the last byte of the tile: the lookahead is discarded).
-    // On entry `s` is the word of the home slot `a` of the key (t, RC).
-#define SLZW_STEP(RC, RN)                                                                       \
+    // One byte of encoder.rs:313-337.  RC = record of this byte (tile index i + OFF), RN = record
+    // of the next byte (anything addressable when this is the last byte of the tile: the
+    // lookahead is discarded).  On entry `s` is the word of the home slot `a` of the key (t, RC).
+#define SLZW_STEP(RC, RN, OFF)                                                                  \
     {                                                                                           \
         const uint32_t an = ((s << 2) & kIdxMask4) ^ (RN).y;                                    \
         const uint32_t sn = tbl_ld(an);    /* speculative: assumes this byte hits */            \
@@ -178,51 +217,100 @@ __device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const u
                     tbl_st(a, key | ncs);                                                       \
                     ncs = (ncs + kScr) & 0xFFFu;                                                \
                     until--;                                                                    \
-                    if (!FIXED && until == 0u) { /* new index == mask, encoder.rs:326 */        \
-                        if (ws < 12u) {          /* encoder.rs:327-328 */                       \
-                            ws++;                                                               \
-                            wtag = ws << 12;                                                    \
-                            const uint32_t nm = (1u << ws) - inc;                               \
-                            until = nm - mask;                                                  \
-                            mask = nm;                                                          \
-                        } else { /* encoder.rs:329-333: clear at 12 bits, dictionary restarts */ \
-                            codes[cp++] = (uint16_t)(scr(clear_code) | (12u << 12));            \
-                            ws = cs + 1u;                                                       \
-                            wtag = ws << 12;                                                    \
-                            mask = (1u << ws) - inc;                                            \
-                            until = mask - first_code + 1u;                                     \
-                            ncs = scr(first_code);                                              \
-                            __syncwarp();                                                       \
-                            clear_table(table, lane);                                           \
-                            __syncwarp();                                                       \
-                        }                                                                       \
-                    }                                                                           \
+                    if (!FIXED && until == 0u) SLZW_BUMP()                                      \
                 }                                                                               \
                 t = (RC).x * (kScr << 8); /* prefix = this byte: (k * kScr mod 4096) << 20 */   \
+                if (kWideMissRuns && lastmiss + 1u == i + (OFF) && i + (OFF) + 1u < len) {      \
+                    i += (OFF) + 1u;                                                            \
+                    goto wide;                                                                  \
+                }                                                                               \
+                lastmiss = i + (OFF);                                                           \
             }                                                                                   \
             a = ((t >> 18) & kIdxMask4) ^ (RN).y;                                               \
             s = tbl_ld(a);                                                                      \
         }                                                                                       \
     }
 
-    uint32_t i = 0;
+restart:
+    if (i >= len) goto done;
+    r0 = rec[i];
+    a = (t >> 18) ^ r0.y;  // home slot of (prefix, byte i); t >> 18 == prefix' << 2
+    s = tbl_ld(a);
     while (i + 4u <= len) {
         const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
-        SLZW_STEP(r0, r1)
-        SLZW_STEP(r1, r2)
-        SLZW_STEP(r2, r3)
-        SLZW_STEP(r3, r4)
+        SLZW_STEP(r0, r1, 0u)
+        SLZW_STEP(r1, r2, 1u)
+        SLZW_STEP(r2, r3, 2u)
+        SLZW_STEP(r3, r4, 3u)
         r0 = r4;
         i += 4u;
     }
     while (i < len) {
         const uint2 r1 = rec[i + 1];
-        SLZW_STEP(r0, r1)
+        SLZW_STEP(r0, r1, 0u)
         r0 = r1;
         i += 1u;
     }
-#undef SLZW_STEP
+    goto done;
 
+wide: {
+        // bytes i .. i+L-1, lane j owns byte i+j; its prefix is byte i+j-1 (lane 0: t)
+        const bool inserting = !FIXED || until != 0u;
+        uint32_t L = len - i < (uint32_t)kWarpSize ? len - i : (uint32_t)kWarpSize;
+        if (inserting && until < L) L = until;
+        const bool on = (uint32_t)lane < L;
+        const uint32_t idx = on ? i + (uint32_t)lane : i;
+        const uint2 rc = rec[idx];
+        uint32_t tj = t;
+        if (on && lane > 0) tj = rec[idx - 1u].x * (kScr << 8);
+        const uint32_t key = tj | rc.x;
+        uint32_t al = (tj >> 18) ^ rc.y;
+        bool found = false;
+        if (on) {
+            for (int guard = 0; guard < kSlots; guard++) {  // private linear probing
+                const uint32_t v = tbl_ld(al);
+                if (v == 0u) break;
+                if (((v ^ key) >> 12) == 0u) {
+                    found = true;
+                    break;
+                }
+                al = tb | ((al + 4u) & kIdxMask4);
+            }
+        }
+        const uint32_t hm = __ballot_sync(kFullMask, on && found);
+        uint32_t cnt = hm ? (uint32_t)__ffs(hm) - 1u : L;  // lanes in front of the first hit
+        if (inserting) {
+            // two lanes that claim the same empty slot: the later one has to look again
+            const uint32_t peers =
+                __match_any_sync(kFullMask, (uint32_t)lane < cnt ? al : (0x80000000u | (uint32_t)lane));
+            const uint32_t cm = __ballot_sync(kFullMask, (uint32_t)lane < cnt &&
+                                                             (peers & ((1u << lane) - 1u)) != 0u);
+            if (cm) cnt = (uint32_t)__ffs(cm) - 1u;
+        }
+        if ((uint32_t)lane < cnt) {
+            codes[cp + (uint32_t)lane] = (uint16_t)((tj >> 20) | wtag);
+            if (inserting) tbl_st(al, key | ((ncs + (uint32_t)lane * kScr) & 0xFFFu));
+        }
+        __syncwarp();
+        if (cnt) {
+            cp += cnt;
+            t = rec[i + cnt - 1u].x * (kScr << 8);
+            i += cnt;
+            lastmiss = i - 1u;
+            if (inserting) {
+                ncs = (ncs + cnt * kScr) & 0xFFFu;
+                until -= cnt;
+                if (!FIXED && until == 0u) SLZW_BUMP()
+            }
+        } else {
+            lastmiss = 0xFFFFFFF0u;  // byte i hits: back to the chain
+        }
+        goto restart;
+    }
+
+done:
+#undef SLZW_STEP
+#undef SLZW_BUMP
     m.t = t;
     m.ncs = ncs;
     m.ws = ws;
