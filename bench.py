@@ -355,13 +355,17 @@ def run_ours(args):
     if not args.no_e2e:
         h_in = torch.from_numpy(buf).pin_memory().numpy()
         h_dense = torch.empty(int(slots[-1]), dtype=torch.uint8).pin_memory().numpy()
+        h_dec = torch.empty(total, dtype=torch.uint8).pin_memory().numpy()
         e2e_steps = max(1, min(args.steps, 3))
         h2d = d2h = 0
+        # one untimed pass: staging buffers of the host path are allocated on first use
+        dense, doff, st, det = codec.encode_batch_dense(params, h_in, off, out=h_dense)
+        codec.decode_batch(params, dense, doff, off, out=h_dec)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             dense, doff, st, det = codec.encode_batch_dense(params, h_in, off, out=h_dense)
-            dec, dlen, dst, ddet = codec.decode_batch(params, dense, doff, off)
+            dec, dlen, dst, ddet = codec.decode_batch(params, dense, doff, off, out=h_dec)
             h2d += total + dense.size + 3 * 8 * (n + 1)
             d2h += dense.size + total + 8 * (n + 1) + 8 * n + 4 * 4 * n
         torch.cuda.synchronize()

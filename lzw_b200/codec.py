@@ -90,12 +90,15 @@ class Codec:
                     "slzw_compact_device")
 
     # ---- host-resident batches: numpy arrays -----------------------------------------------
-    def _host(self, fn, params, in_buf, in_off, out_off, code_size, what):
+    def _host(self, fn, params, in_buf, in_off, out_off, code_size, what, out=None):
         in_buf = np.ascontiguousarray(in_buf, dtype=np.uint8)
         in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
         out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
         n = in_off.size - 1
-        out = np.zeros(max(int(out_off[-1]), 1), dtype=np.uint8)
+        if out is None:
+            out = np.zeros(max(int(out_off[-1]), 1), dtype=np.uint8)
+        elif out.dtype != np.uint8 or out.size < int(out_off[-1]) or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous uint8 array of at least out_off[-1] bytes")
         out_len = np.zeros(max(n, 1), dtype=np.uint64)
         status = np.zeros(max(n, 1), dtype=np.uint32)
         detail = np.zeros(max(n, 1), dtype=np.uint32)
@@ -144,10 +147,11 @@ class Codec:
         self._check(rc, "slzw_encode_batch_host_dense")
         return out[: int(out_off[-1])], out_off, status[:n], detail[:n]
 
-    def decode_batch(self, params, in_buf, in_off, out_off, code_size=None):
-        """Decodes streams into capacity slots out_off.  Returns (out, out_len, status, detail)."""
+    def decode_batch(self, params, in_buf, in_off, out_off, code_size=None, out=None):
+        """Decodes streams into capacity slots out_off.  `out` may be a preallocated (pinned) uint8
+        array.  Returns (out, out_len, status, detail)."""
         return self._host(self._lib.slzw_decode_batch_host, params, in_buf, in_off, out_off,
-                          code_size, "slzw_decode_batch_host")
+                          code_size, "slzw_decode_batch_host", out=out)
 
     # ---- single stream ------------------------------------------------------------------------
     def encode(self, params: Params, data, cap: int | None = None):

@@ -79,6 +79,44 @@ struct Workspace {
 
 constexpr int kWorkspaces = 4;
 constexpr size_t kQueueWords = 4;
+constexpr int kPipe = 3;
+// host-path chunks: at least this many input/output bytes each (a chunk must amortise the tail
+// of its longest stream), at most kMaxChunks per call
+constexpr uint64_t kChunkBytes = 192ull << 20;
+constexpr uint64_t kMaxChunks = 32;
+
+// A grow-only pinned host allocation (small per-chunk result arrays).
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, bytes + bytes / 8 + 256, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes + bytes / 8 + 256;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostSlot {
+    cudaStream_t stream = nullptr;
+    DevBuf in, out, in_off, out_off, out_len, status, detail, cs, dense, dense_off;
+    PinBuf h_dense_off;
+    void release() {
+        for (DevBuf* b : {&in, &out, &in_off, &out_off, &out_len, &status, &detail, &cs, &dense, &dense_off})
+            b->release();
+        h_dense_off.release();
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
 
 }  // namespace
 
@@ -87,9 +125,11 @@ struct slzw_ctx {
     int num_sms = 0;
     Workspace ws[kWorkspaces];
     int ws_next = 0;
-    // host-path staging (device side)
-    DevBuf d_in, d_out, d_in_off, d_out_off, d_out_len, d_status, d_detail, d_cs, d_dense, d_dense_off;
-    cudaStream_t stream = nullptr;  // host-path stream
+    // host-path staging: kPipe slots, each with its own CUDA stream, so that the H2D copy of one
+    // chunk of streams, the kernels of the previous chunk and the D2H copy of the one before
+    // overlap (PCIe is full duplex)
+    HostSlot pipe[kPipe];
+    uint64_t chunk_bytes = kChunkBytes;
     uint64_t launches = 0;
     int last_decode_ws = -1;  // workspace of the most recent decode call
     char err[256] = {0};
@@ -228,7 +268,28 @@ int run_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, cu
     return finish(ctx, w, stream);
 }
 
-// Host path: stage the whole batch on the device, run, copy back.
+// Splits streams [0, n) into chunks of roughly equal weight (weight[i+1] - weight[i] per stream).
+std::vector<uint64_t> chunk_bounds(const uint64_t* weight, uint64_t n, uint64_t chunk_bytes) {
+    const uint64_t total = weight[n] - weight[0];
+    uint64_t chunks = total / chunk_bytes;
+    if (chunks < 1) chunks = 1;
+    if (chunks > kMaxChunks) chunks = kMaxChunks;
+    if (chunks > n) chunks = n;
+    std::vector<uint64_t> cb;
+    cb.push_back(0);
+    uint64_t i = 0;
+    for (uint64_t c = 1; c < chunks; c++) {
+        const uint64_t target = weight[0] + total / chunks * c;
+        while (i < n && weight[i] < target) i++;
+        if (i > cb.back() && i < n) cb.push_back(i);
+    }
+    cb.push_back(n);
+    return cb;
+}
+
+// Host path: the batch goes through the device in chunks of streams, pipelined over kPipe
+// slots (H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 overlap), results land in the
+// caller's buffers.  Pinned host buffers (slzw_host_alloc) make the copies asynchronous.
 int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op op) {
     if (!ctx) return SLZW_RC_INVALID;
     if (!params_ok(params) || !b) {
@@ -245,57 +306,64 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
     }
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
-    cudaStream_t s = ctx->stream;
-    const uint64_t in_lo = b->in_off[0], in_hi = b->in_off[n];
-    const uint64_t out_lo = needs_out ? b->out_off[0] : 0, out_hi = needs_out ? b->out_off[n] : 0;
-    slzw_batch d = {};
-    {
-        std::lock_guard<std::mutex> lock(ctx->mu);
-        CK(ctx->d_in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
-        CK(ctx->d_out.reserve(out_hi - out_lo + 16), "cudaMalloc(out)");
-        CK(ctx->d_in_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(in_off)");
-        CK(ctx->d_out_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(out_off)");
-        CK(ctx->d_out_len.reserve(sizeof(uint64_t) * n), "cudaMalloc(out_len)");
-        CK(ctx->d_status.reserve(sizeof(uint32_t) * n), "cudaMalloc(status)");
-        CK(ctx->d_detail.reserve(sizeof(uint32_t) * n), "cudaMalloc(detail)");
-        if (b->code_size) CK(ctx->d_cs.reserve(n), "cudaMalloc(code_size)");
+    // chunk by the larger side of the stream (uncompressed bytes)
+    const std::vector<uint64_t> cb =
+        chunk_bounds(needs_out && op == Op::Decode ? b->out_off : b->in_off, n, ctx->chunk_bytes);
+    for (size_t k = 0; k + 1 < cb.size(); k++) {
+        HostSlot& hs = ctx->pipe[k % kPipe];
+        cudaStream_t s = hs.stream;
+        const uint64_t s0 = cb[k], s1 = cb[k + 1], m = s1 - s0;
+        const uint64_t in_lo = b->in_off[s0], in_hi = b->in_off[s1];
+        const uint64_t out_lo = needs_out ? b->out_off[s0] : 0, out_hi = needs_out ? b->out_off[s1] : 0;
+        {
+            std::lock_guard<std::mutex> lock(ctx->mu);
+            CK(hs.in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
+            CK(hs.out.reserve(out_hi - out_lo + 16), "cudaMalloc(out)");
+            CK(hs.in_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(in_off)");
+            CK(hs.out_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(out_off)");
+            CK(hs.out_len.reserve(sizeof(uint64_t) * m), "cudaMalloc(out_len)");
+            CK(hs.status.reserve(sizeof(uint32_t) * m), "cudaMalloc(status)");
+            CK(hs.detail.reserve(sizeof(uint32_t) * m), "cudaMalloc(detail)");
+            if (b->code_size) CK(hs.cs.reserve(m), "cudaMalloc(code_size)");
+        }
+        // Offsets stay absolute: the device copies of in/out are biased by -lo instead.
+        if (in_hi > in_lo)
+            CK(cudaMemcpyAsync(hs.in.p, b->in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
+        CK(cudaMemcpyAsync(hs.in_off.p, b->in_off + s0, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
+           "H2D in_off");
+        if (needs_out)
+            CK(cudaMemcpyAsync(hs.out_off.p, b->out_off + s0, sizeof(uint64_t) * (m + 1),
+                               cudaMemcpyHostToDevice, s), "H2D out_off");
+        if (b->code_size)
+            CK(cudaMemcpyAsync(hs.cs.p, b->code_size + s0, m, cudaMemcpyHostToDevice, s), "H2D code_size");
+        slzw_batch d = {};
+        d.in = (const uint8_t*)hs.in.p - in_lo;
+        d.in_off = (const uint64_t*)hs.in_off.p;
+        d.out = needs_out ? (uint8_t*)hs.out.p - out_lo : nullptr;
+        d.out_off = needs_out ? (const uint64_t*)hs.out_off.p : nullptr;
+        d.out_len = (uint64_t*)hs.out_len.p;
+        d.status = (uint32_t*)hs.status.p;
+        d.detail = (uint32_t*)hs.detail.p;
+        d.code_size = b->code_size ? (const uint8_t*)hs.cs.p : nullptr;
+        d.n = m;
+        int rc = run_device(ctx, params, &d, s, op);
+        if (rc != SLZW_RC_OK) return rc;
+        if (needs_out && out_hi > out_lo)
+            CK(cudaMemcpyAsync(b->out + out_lo, hs.out.p, out_hi - out_lo, cudaMemcpyDeviceToHost, s), "D2H out");
+        CK(cudaMemcpyAsync(b->out_len + s0, hs.out_len.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, s),
+           "D2H out_len");
+        CK(cudaMemcpyAsync(b->status + s0, hs.status.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s),
+           "D2H status");
+        CK(cudaMemcpyAsync(b->detail + s0, hs.detail.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s),
+           "D2H detail");
     }
-    // Offsets stay absolute: the device copies of in/out are biased by -lo instead.
-    if (in_hi > in_lo)
-        CK(cudaMemcpyAsync(ctx->d_in.p, b->in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s),
-           "H2D in");
-    CK(cudaMemcpyAsync(ctx->d_in_off.p, b->in_off, sizeof(uint64_t) * (n + 1),
-                       cudaMemcpyHostToDevice, s), "H2D in_off");
-    if (needs_out)
-        CK(cudaMemcpyAsync(ctx->d_out_off.p, b->out_off, sizeof(uint64_t) * (n + 1),
-                           cudaMemcpyHostToDevice, s), "H2D out_off");
-    if (b->code_size)
-        CK(cudaMemcpyAsync(ctx->d_cs.p, b->code_size, n, cudaMemcpyHostToDevice, s), "H2D code_size");
-    d.in = (const uint8_t*)ctx->d_in.p - in_lo;
-    d.in_off = (const uint64_t*)ctx->d_in_off.p;
-    d.out = needs_out ? (uint8_t*)ctx->d_out.p - out_lo : nullptr;
-    d.out_off = needs_out ? (const uint64_t*)ctx->d_out_off.p : nullptr;
-    d.out_len = (uint64_t*)ctx->d_out_len.p;
-    d.status = (uint32_t*)ctx->d_status.p;
-    d.detail = (uint32_t*)ctx->d_detail.p;
-    d.code_size = b->code_size ? (const uint8_t*)ctx->d_cs.p : nullptr;
-    d.n = n;
-    int rc = run_device(ctx, params, &d, s, op);
-    if (rc != SLZW_RC_OK) return rc;
-    if (needs_out && out_hi > out_lo)
-        CK(cudaMemcpyAsync(b->out + out_lo, ctx->d_out.p, out_hi - out_lo, cudaMemcpyDeviceToHost, s),
-           "D2H out");
-    CK(cudaMemcpyAsync(b->out_len, ctx->d_out_len.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, s),
-       "D2H out_len");
-    CK(cudaMemcpyAsync(b->status, ctx->d_status.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s),
-       "D2H status");
-    CK(cudaMemcpyAsync(b->detail, ctx->d_detail.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s),
-       "D2H detail");
-    CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->pipe[i].stream), "cudaStreamSynchronize");
     return SLZW_RC_OK;
 }
 
-// Host path with dense output: worst-case slots stay on the device, compaction before D2H.
+// Host path with dense output: worst-case slots stay on the device, compaction before D2H, so
+// only encoded bytes cross the bus.  Pipelined like run_host; the host learns a chunk's dense
+// size when its kernels are done, places the chunk behind the previous one and starts its copy.
 int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
                           const uint64_t* in_off, uint64_t n, const uint8_t* code_size,
                           uint64_t align, uint8_t* out_dense, uint64_t out_cap, uint64_t* out_off,
@@ -312,66 +380,89 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     if (align == 0) align = 1;
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
-    cudaStream_t s = ctx->stream;
-    const uint64_t in_lo = in_off[0], in_hi = in_off[n];
     // worst-case slots, 16-byte aligned so that the packer's word stores are aligned
     std::vector<uint64_t> slots(n + 1);
     slots[0] = 0;
     for (uint64_t i = 0; i < n; i++) {
-        const uint64_t b = slzw_encode_bound(params, in_off[i + 1] - in_off[i]);
-        slots[i + 1] = slots[i] + ((b + 15) & ~15ull);
+        const uint64_t bnd = slzw_encode_bound(params, in_off[i + 1] - in_off[i]);
+        slots[i + 1] = slots[i] + ((bnd + 15) & ~15ull);
     }
-    {
-        std::lock_guard<std::mutex> lock(ctx->mu);
-        CK(ctx->d_in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
-        CK(ctx->d_out.reserve(slots[n] + 16), "cudaMalloc(slots)");
-        CK(ctx->d_dense.reserve(slots[n] + align * n + 16), "cudaMalloc(dense)");
-        CK(ctx->d_in_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(in_off)");
-        CK(ctx->d_out_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(out_off)");
-        CK(ctx->d_dense_off.reserve(sizeof(uint64_t) * (n + 1)), "cudaMalloc(dense_off)");
-        CK(ctx->d_out_len.reserve(sizeof(uint64_t) * n), "cudaMalloc(out_len)");
-        CK(ctx->d_status.reserve(sizeof(uint32_t) * n), "cudaMalloc(status)");
-        CK(ctx->d_detail.reserve(sizeof(uint32_t) * n), "cudaMalloc(detail)");
-        if (code_size) CK(ctx->d_cs.reserve(n), "cudaMalloc(code_size)");
-    }
-    if (in_hi > in_lo)
-        CK(cudaMemcpyAsync(ctx->d_in.p, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
-    CK(cudaMemcpyAsync(ctx->d_in_off.p, in_off, sizeof(uint64_t) * (n + 1), cudaMemcpyHostToDevice, s),
-       "H2D in_off");
-    CK(cudaMemcpyAsync(ctx->d_out_off.p, slots.data(), sizeof(uint64_t) * (n + 1),
-                       cudaMemcpyHostToDevice, s), "H2D slots");
-    if (code_size) CK(cudaMemcpyAsync(ctx->d_cs.p, code_size, n, cudaMemcpyHostToDevice, s), "H2D code_size");
-    slzw_batch d = {};
-    d.in = (const uint8_t*)ctx->d_in.p - in_lo;
-    d.in_off = (const uint64_t*)ctx->d_in_off.p;
-    d.out = (uint8_t*)ctx->d_out.p;
-    d.out_off = (const uint64_t*)ctx->d_out_off.p;
-    d.out_len = (uint64_t*)ctx->d_out_len.p;
-    d.status = (uint32_t*)ctx->d_status.p;
-    d.detail = (uint32_t*)ctx->d_detail.p;
-    d.code_size = code_size ? (const uint8_t*)ctx->d_cs.p : nullptr;
-    d.n = n;
-    int rc = run_device(ctx, params, &d, s, Op::Encode);
+    const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->chunk_bytes);
+    const size_t chunks = cb.size() - 1;
+
+    auto enqueue = [&](size_t k) -> int {
+        HostSlot& hs = ctx->pipe[k % kPipe];
+        cudaStream_t s = hs.stream;
+        const uint64_t s0 = cb[k], s1 = cb[k + 1], m = s1 - s0;
+        const uint64_t in_lo = in_off[s0], in_hi = in_off[s1];
+        const uint64_t sl_lo = slots[s0], sl_hi = slots[s1];
+        {
+            std::lock_guard<std::mutex> lock(ctx->mu);
+            CK(hs.in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
+            CK(hs.out.reserve(sl_hi - sl_lo + 16), "cudaMalloc(slots)");
+            CK(hs.dense.reserve(sl_hi - sl_lo + align * m + 16), "cudaMalloc(dense)");
+            CK(hs.in_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(in_off)");
+            CK(hs.out_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(out_off)");
+            CK(hs.dense_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(dense_off)");
+            CK(hs.out_len.reserve(sizeof(uint64_t) * m), "cudaMalloc(out_len)");
+            CK(hs.status.reserve(sizeof(uint32_t) * m), "cudaMalloc(status)");
+            CK(hs.detail.reserve(sizeof(uint32_t) * m), "cudaMalloc(detail)");
+            if (code_size) CK(hs.cs.reserve(m), "cudaMalloc(code_size)");
+            CK(hs.h_dense_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaHostAlloc(dense_off)");
+        }
+        if (in_hi > in_lo)
+            CK(cudaMemcpyAsync(hs.in.p, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
+        CK(cudaMemcpyAsync(hs.in_off.p, in_off + s0, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
+           "H2D in_off");
+        CK(cudaMemcpyAsync(hs.out_off.p, slots.data() + s0, sizeof(uint64_t) * (m + 1),
+                           cudaMemcpyHostToDevice, s), "H2D slots");
+        if (code_size) CK(cudaMemcpyAsync(hs.cs.p, code_size + s0, m, cudaMemcpyHostToDevice, s), "H2D code_size");
+        slzw_batch d = {};
+        d.in = (const uint8_t*)hs.in.p - in_lo;
+        d.in_off = (const uint64_t*)hs.in_off.p;
+        d.out = (uint8_t*)hs.out.p - sl_lo;
+        d.out_off = (const uint64_t*)hs.out_off.p;
+        d.out_len = (uint64_t*)hs.out_len.p;
+        d.status = (uint32_t*)hs.status.p;
+        d.detail = (uint32_t*)hs.detail.p;
+        d.code_size = code_size ? (const uint8_t*)hs.cs.p : nullptr;
+        d.n = m;
+        int rc = run_device(ctx, params, &d, s, Op::Encode);
+        if (rc != SLZW_RC_OK) return rc;
+        CK(compact_launch(d.out, d.out_off, d.out_len, m, align, (uint8_t*)hs.dense.p,
+                          (uint64_t*)hs.dense_off.p, ctx->num_sms, s), "compaction launch");
+        ctx->launches += 2;
+        CK(cudaMemcpyAsync(hs.h_dense_off.p, hs.dense_off.p, sizeof(uint64_t) * (m + 1),
+                           cudaMemcpyDeviceToHost, s), "D2H dense_off");
+        CK(cudaMemcpyAsync(status + s0, hs.status.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H status");
+        CK(cudaMemcpyAsync(detail + s0, hs.detail.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H detail");
+        return SLZW_RC_OK;
+    };
+
+    uint64_t hbase = 0;  // dense bytes placed so far
+    bool overflow = false;
+    int rc = enqueue(0);
     if (rc != SLZW_RC_OK) return rc;
-    CK(compact_launch((const uint8_t*)ctx->d_out.p, (const uint64_t*)ctx->d_out_off.p,
-                      (const uint64_t*)ctx->d_out_len.p, n, align, (uint8_t*)ctx->d_dense.p,
-                      (uint64_t*)ctx->d_dense_off.p, ctx->num_sms, s), "compaction launch");
-    ctx->launches += 2;
-    CK(cudaMemcpyAsync(out_off, ctx->d_dense_off.p, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost, s),
-       "D2H dense_off");
-    CK(cudaMemcpyAsync(status, ctx->d_status.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s), "D2H status");
-    CK(cudaMemcpyAsync(detail, ctx->d_detail.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, s), "D2H detail");
-    CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
-    const uint64_t total = out_off[n];
-    if (needed) *needed = total;
-    if (total > out_cap) {
-        snprintf(ctx->err, sizeof ctx->err, "dense output needs %llu bytes, capacity is %llu",
-                 (unsigned long long)total, (unsigned long long)out_cap);
-        return SLZW_RC_NOMEM;
+    for (size_t k = 0; k < chunks; k++) {
+        if (k + 1 < chunks && (rc = enqueue(k + 1)) != SLZW_RC_OK) return rc;
+        HostSlot& hs = ctx->pipe[k % kPipe];
+        CK(cudaStreamSynchronize(hs.stream), "cudaStreamSynchronize");
+        const uint64_t s0 = cb[k], m = cb[k + 1] - cb[k];
+        const uint64_t* rel = (const uint64_t*)hs.h_dense_off.p;
+        const uint64_t total = rel[m];
+        for (uint64_t i = 1; i <= m; i++) out_off[s0 + i] = hbase + rel[i];
+        if (hbase + total > out_cap) overflow = true;
+        if (!overflow && total)
+            CK(cudaMemcpyAsync(out_dense + hbase, hs.dense.p, total, cudaMemcpyDeviceToHost, hs.stream),
+               "D2H dense");
+        hbase += total;
     }
-    if (total) {
-        CK(cudaMemcpyAsync(out_dense, ctx->d_dense.p, total, cudaMemcpyDeviceToHost, s), "D2H dense");
-        CK(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->pipe[i].stream), "cudaStreamSynchronize");
+    if (needed) *needed = hbase;
+    if (overflow) {
+        snprintf(ctx->err, sizeof ctx->err, "dense output needs %llu bytes, capacity is %llu",
+                 (unsigned long long)hbase, (unsigned long long)out_cap);
+        return SLZW_RC_NOMEM;
     }
     return SLZW_RC_OK;
 }
@@ -420,12 +511,22 @@ int slzw_create(int device, slzw_ctx** out) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SLZW_ENC_CONFIG")) encode_select_config(atoi(e));  // tuning knob
+    if (const char* e = getenv("SLZW_HOST_CHUNK_BYTES")) {
+        const long long v = atoll(e);  // tests use tiny chunks
+        if (v > 0) ctx->chunk_bytes = (uint64_t)v;
+    }
     DeviceGuard guard(device);
     if (!guard.ok || encode_configure() != cudaSuccess || decode_exact_configure() != cudaSuccess ||
-        decode_fast_configure() != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        decode_fast_configure() != cudaSuccess) {
         delete ctx;
         return SLZW_RC_CUDA;
+    }
+    for (int i = 0; i < kPipe; i++) {
+        if (cudaStreamCreateWithFlags(&ctx->pipe[i].stream, cudaStreamNonBlocking) != cudaSuccess) {
+            for (int j = 0; j < kPipe; j++) ctx->pipe[j].release();
+            delete ctx;
+            return SLZW_RC_CUDA;
+        }
     }
     *out = ctx;
     return SLZW_RC_OK;
@@ -443,10 +544,7 @@ void slzw_destroy(slzw_ctx* ctx) {
             w.retry.release();
             if (w.done) cudaEventDestroy(w.done);
         }
-        for (DevBuf* b : {&ctx->d_in, &ctx->d_out, &ctx->d_in_off, &ctx->d_out_off, &ctx->d_out_len,
-                          &ctx->d_status, &ctx->d_detail, &ctx->d_cs, &ctx->d_dense, &ctx->d_dense_off})
-            b->release();
-        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        for (int i = 0; i < kPipe; i++) ctx->pipe[i].release();
     }
     delete ctx;
 }

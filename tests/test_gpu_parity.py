@@ -394,3 +394,78 @@ def test_config3_scaled_down_vs_oracle(codec):
     assert ok.mean() > 0.95
     for i in np.nonzero(ok)[0]:
         assert np.array_equal(dec[int(off[i]):int(off[i + 1])], buf[int(off[i]):int(off[i + 1])])
+
+
+# ---- host pipeline (chunked H2D / kernels / D2H) -----------------------------------------------
+def test_host_paths_with_many_small_chunks(monkeypatch):
+    """The host entry points split a batch into chunks of streams and pipeline them over three
+    CUDA streams; with a tiny chunk size every code path of that pipeline runs on a small batch."""
+    import lzw_b200
+    monkeypatch.setenv("SLZW_HOST_CHUNK_BYTES", "20000")
+    c = lzw_b200.Codec(0)
+    try:
+        for p in (O.tiff(), O.gif(5), O.fixed(True)):
+            buf, off = T.make_batch(99, 200, T.max_symbol(p), max_len=9000)
+            slots = np.zeros(off.size, dtype=np.uint64)
+            slots[1:] = np.cumsum([O.encode_bound(int(l)) + 3 for l in np.diff(off)])
+            out, _, out_len, st, det = c.encode_batch(gp(p), buf, off, out_off=slots)
+            o_out, o_len, o_st, o_det = O.encode_batch(p, buf, off, slots)
+            assert np.array_equal(out_len, o_len) and np.array_equal(st, o_st) and np.array_equal(det, o_det)
+            assert T.slots_equal(out, o_out, slots, o_len) == -1
+            dense, doff, st2, det2 = c.encode_batch_dense(gp(p), buf, off, align=2)
+            assert np.array_equal(st2, o_st)
+            for i in range(o_len.size):
+                assert np.array_equal(dense[int(doff[i]):int(doff[i]) + int(o_len[i])],
+                                      o_out[int(slots[i]):int(slots[i]) + int(o_len[i])]), i
+            d_in, d_off = T.pack_dense(o_out, slots, o_len)
+            dec, dlen, dst, ddet = c.decode_batch(gp(p), d_in, d_off, off)
+            o_dec, o_dlen, o_dst, o_ddet = O.decode_batch(p, d_in, d_off, off)
+            assert np.array_equal(dlen, o_dlen) and np.array_equal(dst, o_dst) and np.array_equal(ddet, o_ddet)
+            assert T.slots_equal(dec, o_dec, off, o_dlen) == -1
+    finally:
+        c.close()
+
+
+# ---- fast decoder: deferral to the exact kernel ---------------------------------------------------
+def test_fast_decoder_defers_what_it_cannot_reproduce(codec):
+    """Slots larger than 1 MiB (20-bit offsets), a first code that is not a root (stale-table
+    semantics, decoder.rs:230-236) and a missing clear code go to the exact kernel; the result
+    still equals the oracle's, and the diagnostics name the deferred streams."""
+    rng = np.random.default_rng(5)
+    p = O.tiff()
+    big = T.make_stream(rng, "runs", 1_300_000, 255).tobytes()           # output > 1 MiB
+    st, _, big_packed = O.encode(p, big)
+    assert st == 0
+    small = T.make_stream(rng, "text", 5000, 255).tobytes()
+    _, _, small_packed = O.encode(p, small)
+    streams = [big_packed, small_packed, T.BAD_TIFF]
+    off = np.zeros(len(streams) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(s) for s in streams])
+    data = np.frombuffer(b"".join(streams), dtype=np.uint8)
+    caps = np.zeros(len(streams) + 1, dtype=np.uint64)
+    caps[1:] = np.cumsum([len(big) + 64, len(small) + 64, 4096])
+    dec, dlen, dst, ddet = codec.decode_batch(gp(p), data, off, caps)
+    o_dec, o_dlen, o_dst, o_ddet = O.decode_batch(p, data, off, caps)
+    assert np.array_equal(dlen, o_dlen) and np.array_equal(dst, o_dst) and np.array_equal(ddet, o_ddet)
+    assert T.slots_equal(dec, o_dec, caps, o_dlen) == -1
+    assert int(o_dst[2]) == O.ERR_UNEXPECTED_CODE and int(o_ddet[2]) == 258   # decoder.rs:759-769
+    deferred = set(int(i) for i in codec.last_deferred())
+    assert 0 in deferred and 1 not in deferred
+
+
+def test_fast_decoder_long_words_and_in_step_sources(codec):
+    """Highly repetitive streams: words longer than the 1 KiB step window (periodic copy), chains
+    of codes that name entries created in the same step (KwKwK, decoder.rs:244-250)."""
+    cases = []
+    for p in (O.tiff(), O.gif(2), O.gif(8), O.fixed(False), O.variable(3, True, False)):
+        hi = T.max_symbol(p)
+        cases.append((p, bytes(900_000)))
+        cases.append((p, bytes([1 % (hi + 1), 2 % (hi + 1)]) * 300_000))
+        cases.append((p, bytes([3 % (hi + 1)]) * 17 + bytes([0]) * 70_000 + bytes([1]) * 70_000))
+    for p, raw in cases:
+        st, _, packed = O.encode(p, raw)
+        assert st == 0
+        got = codec.decode(gp(p), packed, cap=len(raw))
+        want = O.decode(p, packed, cap=len(raw))
+        assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], T.pname(p)
+        assert len(codec.last_deferred()) == 0 or want[0] != 0
