@@ -469,3 +469,50 @@ def test_fast_decoder_long_words_and_in_step_sources(codec):
         want = O.decode(p, packed, cap=len(raw))
         assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], T.pname(p)
         assert len(codec.last_deferred()) == 0 or want[0] != 0
+
+
+# ---- BASELINE configs 4 and 5 at (scaled) full stream sizes ----------------------------------------
+def _roundtrip_properties(codec, p, buf, off, code_size=None, oracle_streams=8):
+    """Size-independent properties at full stream size: every stream encodes OK, the decoder
+    returns exactly the input (SURVEY F1 streams: right bytes, error status allowed), compressed
+    sizes and bytes equal the oracle's on a sample of streams."""
+    out, out_off, out_len, st, det = codec.encode_batch(gp(p), buf, off, code_size=code_size)
+    assert (st == 0).all()
+    dense, doff = T.pack_dense(out, out_off, out_len)
+    dec, dlen, dst, ddet = codec.decode_batch(gp(p), dense, doff, off, code_size=code_size)
+    assert np.array_equal(dlen, np.diff(off))
+    assert np.array_equal(dec[: int(off[-1])], buf)
+    assert (dst == 0).mean() > 0.9 and set(np.unique(dst)) <= {0, O.ERR_IO_UNEXPECTED_EOF, O.ERR_UNEXPECTED_CODE}
+    m = min(oracle_streams, off.size - 1)
+    idx = np.linspace(0, off.size - 2, m).astype(int)
+    for i in idx:
+        q = O.Params(p.flavour, int(code_size[i]) if code_size is not None else p.code_size, p.big_endian,
+                     p.tiff_early_change)
+        raw = buf[int(off[i]):int(off[i + 1])].tobytes()
+        o_st, _, o_packed = O.encode(q, raw)
+        assert o_st == 0
+        assert dense[int(doff[i]):int(doff[i + 1])].tobytes() == o_packed, i
+        o_dst, o_ddet, o_raw = O.decode(q, o_packed, cap=len(raw))
+        assert (int(dst[i]), int(ddet[i])) == (o_dst, o_ddet) and o_raw == raw
+    return int(doff[-1])
+
+
+def test_config4_gif_frames_full_size(codec):
+    """Config 4 (scaled to 28 frames): 1024x1024 8-bit-palette GIF frames, code size 2..8 per
+    stream in one batch; 1 MiB outputs sit exactly at the fast decoder's 20-bit offset limit."""
+    from lzw_b200 import workloads as W
+    buf, off, cs = W.gif_frames(28)
+    comp = _roundtrip_properties(codec, O.gif(8), buf, off, code_size=cs, oracle_streams=7)
+    assert 0 < comp < buf.size
+    assert len(codec.last_deferred()) == 0
+
+
+def test_config5_fixed_text_chunks_full_size(codec):
+    """Config 5 (scaled to 1,024 chunks): lorem-like text in 64 KiB chunks, fixed 12-bit codes,
+    both bit orders; the dictionary freezes at 4096 entries (encoder.rs:645-647)."""
+    from lzw_b200 import workloads as W
+    buf, off = W.text_chunks(1024, corpus_bytes=4 << 20)
+    for be in (False, True):
+        comp = _roundtrip_properties(codec, O.fixed(be), buf, off, oracle_streams=6)
+        assert 0 < comp < buf.size
+        assert len(codec.last_deferred()) == 0
