@@ -319,6 +319,170 @@ done:
     m.ncodes = cp;
 }
 
+// ---- tensor memory as a second dictionary store ------------------------------------------------
+// Shared memory holds twelve 16 KB dictionaries per SM and nothing else limits the number of
+// streams in flight.  The SM's 256 KB of tensor memory (512 columns x 128 lanes x 32 bit) is idle
+// in this kernel, so sixteen more warps keep their dictionary there: warp w owns the 32 lanes of
+// its lane quarter (w % 4, the only ones a warp can address) and 128 columns, one column = 32
+// slots.  A probe is `tcgen05.ld.32x32b.x1` of the slot's column (every lane receives its lane's
+// word) plus a shuffle from the slot's lane; the words of the column double as the collision
+// window (the probe sequence is the home slot, then the rest of its column in lane order, then
+// the following columns), and an insert stores the column back with one lane's word replaced.
+__device__ __forceinline__ uint32_t tmem_ld(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(v) : "r"(taddr));
+    return v;
+}
+// The loaded register may only be read after the wait; tying it to the statement keeps the
+// compiler from scheduling a use above it.
+__device__ __forceinline__ void tmem_wait_ld(uint32_t& v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : "+r"(v)::"memory");
+}
+__device__ __forceinline__ void tmem_st(uint32_t taddr, uint32_t v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n" ::"r"(taddr), "r"(v));
+}
+__device__ __forceinline__ void tmem_wait_st() {
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+}
+// zeroes the 128 columns of this warp's dictionary
+__device__ __forceinline__ void tmem_clear(uint32_t tbase) {
+    const uint32_t z = 0u;
+#pragma unroll
+    for (uint32_t c = 0; c < 128u; c += 16u)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+                     "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(tbase + c),
+                     "r"(z));
+    tmem_wait_st();
+}
+
+// match_tile for a dictionary in tensor memory.  rec[i] = {byte << 12, dictionary's tensor-memory
+// address | 7 hash bits of the byte}: the column of the key (prefix, byte) is
+// (prefix' & 127) ^ hash7(byte), its lane is prefix' >> 7.  Same speculative structure as the
+// shared-memory loop: the column of byte i+1 is requested (assuming byte i hits) before byte i's
+// comparison resolves.
+template <bool FIXED>
+__device__ __forceinline__ void match_tile_tmem(const uint32_t tbase, const uint2* __restrict__ rec,
+                                                uint16_t* __restrict__ codes, const int lane,
+                                                const uint32_t len, MatchState& m,
+                                                const uint32_t cs, const uint32_t inc,
+                                                const uint32_t clear_code,
+                                                const uint32_t first_code) {
+    uint32_t t = m.t;
+    uint32_t ncs = m.ncs;
+    uint32_t ws = FIXED ? 12u : m.ws;
+    uint32_t wtag = ws << 12;
+    uint32_t mask = m.mask;
+    uint32_t until = m.until;
+    uint32_t cp = m.ncodes;
+
+    uint2 r0 = rec[0];
+    uint32_t a = ((t >> 20) & 0x7Fu) ^ r0.y;  // column of (prefix, byte 0)
+    uint32_t hl = t >> 27;                    // its lane
+    uint32_t cl = tmem_ld(a);                 // this lane's word of that column
+    tmem_wait_ld(cl);
+    uint32_t s = __shfl_sync(kFullMask, cl, hl);
+
+#define SLZW_STEP_T(RC, RN)                                                                     \
+    {                                                                                           \
+        const uint32_t an = (s & 0x7Fu) ^ (RN).y;                                               \
+        uint32_t cn = tmem_ld(an);         /* speculative: assumes this byte hits */            \
+        const uint32_t x = s ^ t ^ (RC).x; /* == code' iff the slot holds this key */           \
+        tmem_wait_ld(cn);                                                                       \
+        if (x - 1u < 4095u) {              /* find_word hit, encoder.rs:319-320 */              \
+            t = s << 20;                                                                        \
+            hl = (s >> 7) & 31u;                                                                \
+            a = an;                                                                             \
+            cl = cn;                                                                            \
+            s = __shfl_sync(kFullMask, cn, hl);                                                 \
+        } else {                                                                                \
+            const uint32_t key = t | (RC).x;                                                    \
+            bool hit = false;                                                                   \
+            uint32_t pos = hl;                                                                  \
+            if (s != 0u) { /* another key at home: the column, then the following columns */    \
+                uint32_t start = hl;                                                            \
+                for (int round = 0; round < 129; round++) {                                     \
+                    const uint32_t mm =                                                         \
+                        __ballot_sync(kFullMask, ((cl ^ key) >> 12) == 0u && cl != 0u);         \
+                    const uint32_t me = __ballot_sync(kFullMask, cl == 0u);                     \
+                    const uint32_t stop = mm | me;                                              \
+                    const uint32_t rot = __funnelshift_r(stop, stop, start);                    \
+                    if (rot) {                                                                  \
+                        pos = (start + (uint32_t)__ffs(rot) - 1u) & 31u;                        \
+                        hit = (mm >> pos) & 1u;                                                 \
+                        break;                                                                  \
+                    }                                                                           \
+                    a = (a & ~0x7Fu) | ((a + 1u) & 0x7Fu);                                      \
+                    start = 0u;                                                                 \
+                    cl = tmem_ld(a);                                                            \
+                    tmem_wait_ld(cl);                                                           \
+                }                                                                               \
+            }                                                                                   \
+            if (hit) {                                                                          \
+                s = __shfl_sync(kFullMask, cl, pos);                                            \
+                t = s << 20;                                                                    \
+            } else {                                                                            \
+                /* miss: encoder.rs:322-324 / 645-649 */                                        \
+                codes[cp++] = (uint16_t)((t >> 20) | wtag);                                     \
+                if (!FIXED || until != 0u) {                                                    \
+                    if ((uint32_t)lane == pos) cl = key | ncs;                                  \
+                    tmem_st(a, cl);                                                             \
+                    tmem_wait_st();                                                             \
+                    ncs = (ncs + kScr) & 0xFFFu;                                                \
+                    until--;                                                                    \
+                    if (!FIXED && until == 0u) { /* new index == mask, encoder.rs:326 */        \
+                        if (ws < 12u) {          /* encoder.rs:327-328 */                       \
+                            ws++;                                                               \
+                            wtag = ws << 12;                                                    \
+                            const uint32_t nm = (1u << ws) - inc;                               \
+                            until = nm - mask;                                                  \
+                            mask = nm;                                                          \
+                        } else { /* encoder.rs:329-333 */                                       \
+                            codes[cp++] = (uint16_t)(scr(clear_code) | (12u << 12));            \
+                            ws = cs + 1u;                                                       \
+                            wtag = ws << 12;                                                    \
+                            mask = (1u << ws) - inc;                                            \
+                            until = mask - first_code + 1u;                                     \
+                            ncs = scr(first_code);                                              \
+                            tmem_clear(tbase);                                                  \
+                        }                                                                       \
+                    }                                                                           \
+                }                                                                               \
+                t = (RC).x * (kScr << 8); /* prefix = this byte */                              \
+            }                                                                                   \
+            a = ((t >> 20) & 0x7Fu) ^ (RN).y;                                                   \
+            hl = t >> 27;                                                                       \
+            cl = tmem_ld(a);                                                                    \
+            tmem_wait_ld(cl);                                                                   \
+            s = __shfl_sync(kFullMask, cl, hl);                                                 \
+        }                                                                                       \
+    }
+
+    uint32_t i = 0;
+    while (i + 4u <= len) {
+        const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
+        SLZW_STEP_T(r0, r1)
+        SLZW_STEP_T(r1, r2)
+        SLZW_STEP_T(r2, r3)
+        SLZW_STEP_T(r3, r4)
+        r0 = r4;
+        i += 4u;
+    }
+    while (i < len) {
+        const uint2 r1 = rec[i + 1];
+        SLZW_STEP_T(r0, r1)
+        r0 = r1;
+        i += 1u;
+    }
+#undef SLZW_STEP_T
+
+    m.t = t;
+    m.ncs = ncs;
+    m.ws = ws;
+    m.mask = mask;
+    m.until = until;
+    m.ncodes = cp;
+}
+
 // The 32-bit word of lane `lane` of the tile whose first byte is at `p` (skew = p & 3): the
 // aligned word at p - skew + 4 * lane, or 0 when it holds no byte of [p, p + tile_len).  An
 // aligned word that holds at least one byte of the stream is read whole.
@@ -330,7 +494,9 @@ __device__ __forceinline__ uint32_t load_tile_word(const uint8_t* __restrict__ p
     return 0u;
 }
 
-template <int TILE, bool FIXED>
+// TMEM = the stream's dictionary lives in tensor memory at address `tb` (table is unused);
+// otherwise `table` / `tb` are the generic pointer and the shared-window address of its 16 KB.
+template <int TILE, bool FIXED, bool TMEM>
 __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restrict__ table,
                               const uint32_t tb, EncMisc<TILE>& S, int lane) {
     using Misc = EncMisc<TILE>;
@@ -368,7 +534,8 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     uint32_t tile_len = (uint32_t)((n - pos) < (uint64_t)(TILE - skew) ? (n - pos) : (TILE - skew));
     uint32_t w = tile_len ? load_tile_word(src + pos, skew, tile_len, lane) : 0u;
 
-    clear_table(table, lane);
+    if constexpr (TMEM) tmem_clear(tb);
+    else clear_table(table, lane);
     for (int i = lane; i < Misc::kOutWords; i += kWarpSize) outw[i] = 0;
 
     const uint32_t max_code = (1u << cs) - 1;  // encoder.rs:285
@@ -472,7 +639,8 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
             const uint32_t idx = 4u * (uint32_t)lane + (uint32_t)b - skew;  // wraps before the tile
             const uint32_t k = (w >> (8 * b)) & 0xFFu;
             if (idx < tile_len) {
-                rec[idx] = make_uint2(k << 12, tb | (((k * kByteMul) << 2) & kIdxMask4));
+                rec[idx] = make_uint2(k << 12, TMEM ? (tb | (((k * kByteMul) >> 2) & 0x7Fu))
+                                                    : (tb | (((k * kByteMul) << 2) & kIdxMask4)));
                 if (!FIXED && k > max_code && idx < bad) bad = idx;
             }
         }
@@ -490,8 +658,12 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
         const uint32_t wn = nlen ? load_tile_word(src + npos, 0u, nlen, lane) : 0u;
         __syncwarp();
 
-        if (len)
-            match_tile<FIXED>(table, tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
+        if (len) {
+            if constexpr (TMEM)
+                match_tile_tmem<FIXED>(tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
+            else
+                match_tile<FIXED>(table, tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
+        }
         __syncwarp();
 
         pack_and_flush(m.ncodes);
@@ -545,13 +717,15 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     __syncwarp();
 }
 
-// Shared-memory layout of the CTA (dynamic shared memory, base address `base` in the shared
-// window): the dictionaries start at the first 16 KB boundary; the per-warp EncMisc blocks fill
-// the gap in front of it and continue behind the last dictionary.
-template <int TILE, int WARPS>
+// Shared-memory layout of the CTA (dynamic shared memory, `base` = shared-window address of its
+// first usable byte): the SWARPS dictionaries start at the first 16 KB boundary; the per-warp
+// EncMisc blocks of all WARPS warps fill the gap in front of it and continue behind the last
+// dictionary.
+template <int TILE, int SWARPS, int WARPS>
 struct EncLayout {
     static constexpr uint32_t kTable = kSlots * 4;
     static constexpr uint32_t kMisc = (uint32_t)((sizeof(EncMisc<TILE>) + 15) & ~size_t(15));
+    static constexpr uint32_t kHead = 16;  // tensor-memory base address slot
     __host__ __device__ static uint32_t first_table(uint32_t base) {
         return (base + kTable - 1) & ~(kTable - 1);
     }
@@ -562,84 +736,130 @@ struct EncLayout {
     __host__ __device__ static uint32_t misc_addr(uint32_t base, uint32_t warp) {
         const uint32_t front = misc_in_front(base);
         return warp < front ? base + warp * kMisc
-                            : first_table(base) + WARPS * kTable + (warp - front) * kMisc;
+                            : first_table(base) + SWARPS * kTable + (warp - front) * kMisc;
     }
-    __host__ __device__ static uint32_t bytes(uint32_t base) {  // dynamic shared memory needed
+    __host__ __device__ static uint32_t bytes(uint32_t base) {  // bytes needed from `base` on
         const uint32_t front = misc_in_front(base);
-        return first_table(base) - base + WARPS * kTable + (WARPS - front) * kMisc;
+        return first_table(base) - base + SWARPS * kTable + (WARPS - front) * kMisc;
     }
 };
 
-template <int TILE, int WARPS, bool FIXED>
-__global__ void __launch_bounds__(WARPS * kWarpSize, 1)
+// Warps [0, TWARPS) keep their dictionary in tensor memory, warps [TWARPS, TWARPS + SWARPS) in
+// shared memory.
+template <int TILE, int SWARPS, int TWARPS, bool FIXED>
+__global__ void __launch_bounds__((SWARPS + TWARPS) * kWarpSize, 1)
 slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    using L = EncLayout<TILE, WARPS>;
+    constexpr int WARPS = SWARPS + TWARPS;
+    using L = EncLayout<TILE, SWARPS, WARPS>;
+    static_assert(TWARPS == 0 || TWARPS == 16, "tensor memory holds 16 dictionaries of 128 columns");
     const uint32_t warp = threadIdx.x / kWarpSize;
     const int lane = threadIdx.x % kWarpSize;
-    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    if (L::bytes(base) > dyn_bytes) __trap();  // launch configuration and layout disagree
-    const uint32_t tb = L::first_table(base) + warp * L::kTable;
-    uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw + (tb - base));
-    EncMisc<TILE>& S = *reinterpret_cast<EncMisc<TILE>*>(smem_raw + (L::misc_addr(base, warp) - base));
-    for (;;) {
-        unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(a.queue, 1ull);
-        q = __shfl_sync(kFullMask, q, 0);
-        if (q >= a.n) break;
-        const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-        encode_stream<TILE, FIXED>(a, sid, table, tb, S, lane);
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem_raw) + L::kHead;
+    if (L::bytes(base) + L::kHead > dyn_bytes) __trap();  // launch configuration and layout disagree
+
+    uint32_t tmem_base = 0;
+    if constexpr (TWARPS > 0) {
+        if (warp == 0) {  // one warp allocates all 512 columns for the CTA (one CTA per SM)
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(smem_raw)),
+                         "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw);
+    }
+
+    EncMisc<TILE>& S =
+        *reinterpret_cast<EncMisc<TILE>*>(smem_raw + L::kHead + (L::misc_addr(base, warp) - base));
+    if (TWARPS > 0 && warp < (uint32_t)(TWARPS > 0 ? TWARPS : 1)) {
+        // lane quarter warp % 4 (bits 16..), columns 128 * (warp / 4)
+        const uint32_t tb = tmem_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 128u;
+        for (;;) {
+            unsigned long long q = 0;
+            if (lane == 0) q = atomicAdd(a.queue, 1ull);
+            q = __shfl_sync(kFullMask, q, 0);
+            if (q >= a.n) break;
+            const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
+            encode_stream<TILE, FIXED, true>(a, sid, nullptr, tb, S, lane);
+        }
+    } else {
+        const uint32_t tb = L::first_table(base) + (warp - TWARPS) * L::kTable;
+        uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw + L::kHead + (tb - base));
+        for (;;) {
+            unsigned long long q = 0;
+            if (lane == 0) q = atomicAdd(a.queue, 1ull);
+            q = __shfl_sync(kFullMask, q, 0);
+            if (q >= a.n) break;
+            const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
+            encode_stream<TILE, FIXED, false>(a, sid, table, tb, S, lane);
+        }
+    }
+
+    if constexpr (TWARPS > 0) {
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncthreads();
+        if (warp == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
     }
 }
 
 }  // namespace
 
 // ---- launch configuration ---------------------------------------------------------------------
-// {input tile, warps (= streams) per SM}
-template <int TILE, int WARPS>
+// {input tile, warps with a shared-memory dictionary, warps with a tensor-memory dictionary}
+template <int TILE, int SWARPS, int TWARPS>
 struct EncConfig {
-    using L = EncLayout<TILE, WARPS>;
+    using L = EncLayout<TILE, SWARPS, SWARPS + TWARPS>;
     // the shared window of a CTA starts with 1 KB reserved by the system; taking the larger of
     // the two layouts keeps the launch valid should the dynamic region start at 0 instead
     static uint32_t smem() {
-        const uint32_t a = L::bytes(1024u), b = L::bytes(0u);
-        return a > b ? a : b;
+        const uint32_t a = L::bytes(1024u + L::kHead), b = L::bytes(L::kHead);
+        return (a > b ? a : b) + L::kHead;
     }
     static cudaError_t configure() {
-        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, WARPS, false>,
+        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, WARPS, true>,
+        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
     }
     static cudaError_t launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
+        constexpr int WARPS = SWARPS + TWARPS;
         const uint64_t ctas = (a.n + WARPS - 1) / WARPS;
         const int grid = (int)(ctas < (uint64_t)num_sms ? ctas : (uint64_t)num_sms);
         if (a.p.flavour == SLZW_FLAVOUR_FIXED)
-            slzw_encode_kernel<TILE, WARPS, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         else
-            slzw_encode_kernel<TILE, WARPS, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         return cudaGetLastError();
     }
 };
 
-using Enc0 = EncConfig<128, 12>;
-using Enc1 = EncConfig<96, 13>;
-static_assert(sizeof(EncMisc<128>) <= 2048 && sizeof(EncMisc<96>) <= 1280, "EncMisc grew");
+using Enc0 = EncConfig<96, 12, 16>;   // 12 shared-memory + 16 tensor-memory dictionaries per SM
+using Enc1 = EncConfig<128, 12, 0>;   // shared memory only
+using Enc2 = EncConfig<96, 13, 0>;
 
 static int g_enc_config = 0;
 
-void encode_select_config(int c) { g_enc_config = (c == 1) ? 1 : 0; }
-int encode_streams_per_sm() { return g_enc_config == 1 ? 13 : 12; }
+void encode_select_config(int c) { g_enc_config = (c >= 0 && c <= 2) ? c : 0; }
+int encode_streams_per_sm() { return g_enc_config == 0 ? 28 : g_enc_config == 1 ? 12 : 13; }
 
 cudaError_t encode_configure() {
     cudaError_t e = Enc0::configure();
     if (e != cudaSuccess) return e;
-    return Enc1::configure();
+    if ((e = Enc1::configure()) != cudaSuccess) return e;
+    return Enc2::configure();
 }
 
 cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
-    return g_enc_config == 1 ? Enc1::launch(a, num_sms, stream) : Enc0::launch(a, num_sms, stream);
+    switch (g_enc_config) {
+        case 1: return Enc1::launch(a, num_sms, stream);
+        case 2: return Enc2::launch(a, num_sms, stream);
+        default: return Enc0::launch(a, num_sms, stream);
+    }
 }
 
 }  // namespace slzw

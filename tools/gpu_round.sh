@@ -1,8 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest.log
+timeout 120 python tools/tiny_check.py 2>&1 | grep -v Warning | tail -12 | tee gpurun_out/tiny.log
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest.log
 tail -5 gpurun_out/pytest.log
-echo "== config 4, 512 frames" | tee -a gpurun_out/step.log
-timeout 600 python tools/profile_step.py --config 4 --streams 512 --passes 2 2>&1 | grep -v Warning | tee -a gpurun_out/step.log
-echo "== config 5, 16384 chunks" | tee -a gpurun_out/step.log
-timeout 600 python tools/profile_step.py --config 5 --streams 16384 --passes 2 2>&1 | grep -v Warning | tee -a gpurun_out/step.log
+for c in 0 1; do
+  echo "== SLZW_ENC_CONFIG=$c" | tee -a gpurun_out/step.log
+  SLZW_ENC_CONFIG=$c timeout 300 python tools/profile_step.py --streams 16384 --passes 3 --what encode 2>&1 | grep -v Warning | tee -a gpurun_out/step.log
+done
