@@ -113,6 +113,7 @@ __device__ __forceinline__ bool probe_wide(uint32_t tb, uint32_t key, int lane, 
     uint32_t h4 = a + 4u * (uint32_t)(lane + 1);  // this lane's slot in the first window
     // the table always keeps empty slots (<= 4091 entries); the bound only keeps a corrupted
     // table from hanging the warp
+#pragma unroll 1
     for (int round = 0; round < kSlots / kWarpSize + 1; round++) {
         const uint32_t v = tbl_ld(tb | (h4 & kIdxMask4));
         const uint32_t bm = __ballot_sync(kFullMask, ((v ^ key) >> 12) == 0u && v != 0u);
@@ -151,7 +152,7 @@ __device__ __forceinline__ void clear_table(uint32_t* table, int lane) {
 //     earlier lane is a miss too and none of them claimed the same slot (an earlier insert can
 //     only change lane j's lookup by filling exactly that slot, which also covers equal keys).
 //     The warp commits the longest such prefix of lanes at once: codes, inserts, counters.
-template <bool FIXED>
+template <bool FIXED, int U>
 __device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const uint32_t tb,
                                            const uint2* __restrict__ rec,
                                            uint16_t* __restrict__ codes, const int lane,
@@ -236,15 +237,28 @@ restart:
     r0 = rec[i];
     a = (t >> 18) ^ r0.y;  // home slot of (prefix, byte i); t >> 18 == prefix' << 2
     s = tbl_ld(a);
-    while (i + 4u <= len) {
-        const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
-        SLZW_STEP(r0, r1, 0u)
-        SLZW_STEP(r1, r2, 1u)
-        SLZW_STEP(r2, r3, 2u)
-        SLZW_STEP(r3, r4, 3u)
-        r0 = r4;
-        i += 4u;
+    // U = unrolling of the step: 4 saves loop overhead, 1 keeps the hot code small (28 warps of
+    // two kernel variants share the SM's instruction caches)
+    if constexpr (U >= 4) {
+        while (i + 4u <= len) {
+            const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
+            SLZW_STEP(r0, r1, 0u)
+            SLZW_STEP(r1, r2, 1u)
+            SLZW_STEP(r2, r3, 2u)
+            SLZW_STEP(r3, r4, 3u)
+            r0 = r4;
+            i += 4u;
+        }
+    } else if constexpr (U >= 2) {
+        while (i + 2u <= len) {
+            const uint2 r1 = rec[i + 1], r2 = rec[i + 2];
+            SLZW_STEP(r0, r1, 0u)
+            SLZW_STEP(r1, r2, 1u)
+            r0 = r2;
+            i += 2u;
+        }
     }
+#pragma unroll 1
     while (i < len) {
         const uint2 r1 = rec[i + 1];
         SLZW_STEP(r0, r1, 0u)
@@ -360,7 +374,7 @@ __device__ __forceinline__ void tmem_clear(uint32_t tbase) {
 // (prefix' & 127) ^ hash7(byte), its lane is prefix' >> 7.  Same speculative structure as the
 // shared-memory loop: the column of byte i+1 is requested (assuming byte i hits) before byte i's
 // comparison resolves.
-template <bool FIXED>
+template <bool FIXED, int U>
 __device__ __forceinline__ void match_tile_tmem(const uint32_t tbase, const uint2* __restrict__ rec,
                                                 uint16_t* __restrict__ codes, const int lane,
                                                 const uint32_t len, MatchState& m,
@@ -400,7 +414,7 @@ __device__ __forceinline__ void match_tile_tmem(const uint32_t tbase, const uint
             uint32_t pos = hl;                                                                  \
             if (s != 0u) { /* another key at home: the column, then the following columns */    \
                 uint32_t start = hl;                                                            \
-                for (int round = 0; round < 129; round++) {                                     \
+                _Pragma("unroll 1") for (int round = 0; round < 129; round++) {                 \
                     const uint32_t mm =                                                         \
                         __ballot_sync(kFullMask, ((cl ^ key) >> 12) == 0u && cl != 0u);         \
                     const uint32_t me = __ballot_sync(kFullMask, cl == 0u);                     \
@@ -458,15 +472,26 @@ __device__ __forceinline__ void match_tile_tmem(const uint32_t tbase, const uint
     }
 
     uint32_t i = 0;
-    while (i + 4u <= len) {
-        const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
-        SLZW_STEP_T(r0, r1)
-        SLZW_STEP_T(r1, r2)
-        SLZW_STEP_T(r2, r3)
-        SLZW_STEP_T(r3, r4)
-        r0 = r4;
-        i += 4u;
+    if constexpr (U >= 4) {
+        while (i + 4u <= len) {
+            const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
+            SLZW_STEP_T(r0, r1)
+            SLZW_STEP_T(r1, r2)
+            SLZW_STEP_T(r2, r3)
+            SLZW_STEP_T(r3, r4)
+            r0 = r4;
+            i += 4u;
+        }
+    } else if constexpr (U >= 2) {
+        while (i + 2u <= len) {
+            const uint2 r1 = rec[i + 1], r2 = rec[i + 2];
+            SLZW_STEP_T(r0, r1)
+            SLZW_STEP_T(r1, r2)
+            r0 = r2;
+            i += 2u;
+        }
     }
+#pragma unroll 1
     while (i < len) {
         const uint2 r1 = rec[i + 1];
         SLZW_STEP_T(r0, r1)
@@ -494,11 +519,14 @@ __device__ __forceinline__ uint32_t load_tile_word(const uint8_t* __restrict__ p
     return 0u;
 }
 
-// TMEM = the stream's dictionary lives in tensor memory at address `tb` (table is unused);
-// otherwise `table` / `tb` are the generic pointer and the shared-window address of its 16 KB.
-template <int TILE, bool FIXED, bool TMEM>
+// tmem (warp-uniform) = the stream's dictionary lives in tensor memory at address `tb` (table is
+// unused); otherwise `table` / `tb` are the generic pointer and the shared-window address of its
+// 16 KB.  One function body for both kinds of warp: everything but the match loop is shared, which
+// keeps the instruction footprint of the 28 warps down.
+template <int TILE, bool FIXED, bool HAS_TMEM, int U>
 __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restrict__ table,
-                              const uint32_t tb, EncMisc<TILE>& S, int lane) {
+                              const uint32_t tb, const bool tmem_warp, EncMisc<TILE>& S, int lane) {
+    const bool TMEM = HAS_TMEM && tmem_warp;
     using Misc = EncMisc<TILE>;
     static_assert(TILE % 4 == 0 && TILE <= 4 * kWarpSize, "one 32-bit word per lane");
     uint2* __restrict__ rec = S.rec;
@@ -534,7 +562,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     uint32_t tile_len = (uint32_t)((n - pos) < (uint64_t)(TILE - skew) ? (n - pos) : (TILE - skew));
     uint32_t w = tile_len ? load_tile_word(src + pos, skew, tile_len, lane) : 0u;
 
-    if constexpr (TMEM) tmem_clear(tb);
+    if (TMEM) tmem_clear(tb);
     else clear_table(table, lane);
     for (int i = lane; i < Misc::kOutWords; i += kWarpSize) outw[i] = 0;
 
@@ -659,10 +687,10 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
         __syncwarp();
 
         if (len) {
-            if constexpr (TMEM)
-                match_tile_tmem<FIXED>(tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
+            if (TMEM)
+                match_tile_tmem<FIXED, U>(tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
             else
-                match_tile<FIXED>(table, tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
+                match_tile<FIXED, U>(table, tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
         }
         __syncwarp();
 
@@ -746,7 +774,7 @@ struct EncLayout {
 
 // Warps [0, TWARPS) keep their dictionary in tensor memory, warps [TWARPS, TWARPS + SWARPS) in
 // shared memory.
-template <int TILE, int SWARPS, int TWARPS, bool FIXED>
+template <int TILE, int SWARPS, int TWARPS, int U, bool FIXED>
 __global__ void __launch_bounds__((SWARPS + TWARPS) * kWarpSize, 1)
 slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -774,28 +802,23 @@ slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
 
     EncMisc<TILE>& S =
         *reinterpret_cast<EncMisc<TILE>*>(smem_raw + L::kHead + (L::misc_addr(base, warp) - base));
-    if (TWARPS > 0 && warp < (uint32_t)(TWARPS > 0 ? TWARPS : 1)) {
-        // lane quarter warp % 4 (bits 16..), columns 128 * (warp / 4)
-        const uint32_t tb = tmem_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 128u;
-        for (;;) {
-            unsigned long long q = 0;
-            if (lane == 0) q = atomicAdd(a.queue, 1ull);
-            q = __shfl_sync(kFullMask, q, 0);
-            if (q >= a.n) break;
-            const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-            encode_stream<TILE, FIXED, true>(a, sid, nullptr, tb, S, lane);
-        }
+    const bool tmem_warp = TWARPS > 0 && warp < (uint32_t)(TWARPS > 0 ? TWARPS : 1);
+    uint32_t tb;
+    uint32_t* table = nullptr;
+    if (tmem_warp) {
+        // lane quarter warp % 4 (address bits 16 and up), columns 128 * (warp / 4)
+        tb = tmem_base + (((warp & 3u) * 32u) << 16) + (warp >> 2) * 128u;
     } else {
-        const uint32_t tb = L::first_table(base) + (warp - TWARPS) * L::kTable;
-        uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw + L::kHead + (tb - base));
-        for (;;) {
-            unsigned long long q = 0;
-            if (lane == 0) q = atomicAdd(a.queue, 1ull);
-            q = __shfl_sync(kFullMask, q, 0);
-            if (q >= a.n) break;
-            const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-            encode_stream<TILE, FIXED, false>(a, sid, table, tb, S, lane);
-        }
+        tb = L::first_table(base) + (warp - TWARPS) * L::kTable;
+        table = reinterpret_cast<uint32_t*>(smem_raw + L::kHead + (tb - base));
+    }
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(a.queue, 1ull);
+        q = __shfl_sync(kFullMask, q, 0);
+        if (q >= a.n) break;
+        const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
+        encode_stream<TILE, FIXED, (TWARPS > 0), U>(a, sid, table, tb, tmem_warp, S, lane);
     }
 
     if constexpr (TWARPS > 0) {
@@ -810,7 +833,7 @@ slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
 
 // ---- launch configuration ---------------------------------------------------------------------
 // {input tile, warps with a shared-memory dictionary, warps with a tensor-memory dictionary}
-template <int TILE, int SWARPS, int TWARPS>
+template <int TILE, int SWARPS, int TWARPS, int U>
 struct EncConfig {
     using L = EncLayout<TILE, SWARPS, SWARPS + TWARPS>;
     // the shared window of a CTA starts with 1 KB reserved by the system; taking the larger of
@@ -820,10 +843,10 @@ struct EncConfig {
         return (a > b ? a : b) + L::kHead;
     }
     static cudaError_t configure() {
-        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, false>,
+        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, true>,
+        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
     }
     static cudaError_t launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
@@ -831,33 +854,36 @@ struct EncConfig {
         const uint64_t ctas = (a.n + WARPS - 1) / WARPS;
         const int grid = (int)(ctas < (uint64_t)num_sms ? ctas : (uint64_t)num_sms);
         if (a.p.flavour == SLZW_FLAVOUR_FIXED)
-            slzw_encode_kernel<TILE, SWARPS, TWARPS, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         else
-            slzw_encode_kernel<TILE, SWARPS, TWARPS, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         return cudaGetLastError();
     }
 };
 
-using Enc0 = EncConfig<96, 12, 16>;   // 12 shared-memory + 16 tensor-memory dictionaries per SM
-using Enc1 = EncConfig<128, 12, 0>;   // shared memory only
-using Enc2 = EncConfig<96, 13, 0>;
+using Enc0 = EncConfig<96, 12, 16, 2>;  // 12 shared-memory + 16 tensor-memory dictionaries per SM
+using Enc1 = EncConfig<128, 12, 0, 4>;  // shared memory only
+using Enc2 = EncConfig<96, 12, 16, 4>;
+using Enc3 = EncConfig<96, 12, 16, 1>;
 
 static int g_enc_config = 0;
 
-void encode_select_config(int c) { g_enc_config = (c >= 0 && c <= 2) ? c : 0; }
-int encode_streams_per_sm() { return g_enc_config == 0 ? 28 : g_enc_config == 1 ? 12 : 13; }
+void encode_select_config(int c) { g_enc_config = (c >= 0 && c <= 3) ? c : 0; }
+int encode_streams_per_sm() { return g_enc_config == 1 ? 12 : 28; }
 
 cudaError_t encode_configure() {
     cudaError_t e = Enc0::configure();
     if (e != cudaSuccess) return e;
     if ((e = Enc1::configure()) != cudaSuccess) return e;
-    return Enc2::configure();
+    if ((e = Enc2::configure()) != cudaSuccess) return e;
+    return Enc3::configure();
 }
 
 cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
     switch (g_enc_config) {
         case 1: return Enc1::launch(a, num_sms, stream);
         case 2: return Enc2::launch(a, num_sms, stream);
+        case 3: return Enc3::launch(a, num_sms, stream);
         default: return Enc0::launch(a, num_sms, stream);
     }
 }

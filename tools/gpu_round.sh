@@ -1,9 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python tools/tiny_check.py 2>&1 | grep -v Warning | tail -12 | tee gpurun_out/tiny.log
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 > gpurun_out/pytest.log
-tail -5 gpurun_out/pytest.log
-for c in 0 1; do
+tail -3 gpurun_out/pytest.log
+for c in 0 3 2; do
   echo "== SLZW_ENC_CONFIG=$c" | tee -a gpurun_out/step.log
   SLZW_ENC_CONFIG=$c timeout 300 python tools/profile_step.py --streams 16384 --passes 3 --what encode 2>&1 | grep -v Warning | tee -a gpurun_out/step.log
 done
