@@ -82,7 +82,10 @@ constexpr size_t kQueueWords = 4;
 constexpr int kPipe = 3;
 // host-path chunks: at least this many input/output bytes each (a chunk must amortise the tail
 // of its longest stream), at most kMaxChunks per call
-constexpr uint64_t kChunkBytes = 192ull << 20;
+// measured on config 3 (profiles/r01_e2e_notes.md): the encoder wants larger chunks (every chunk
+// pays the tail of its longest streams at 28 streams per SM), the decoder is copy-bound
+constexpr uint64_t kEncChunkBytes = 384ull << 20;
+constexpr uint64_t kDecChunkBytes = 128ull << 20;
 constexpr uint64_t kMaxChunks = 32;
 
 // A grow-only pinned host allocation (small per-chunk result arrays).
@@ -108,11 +111,11 @@ struct PinBuf {
 struct HostSlot {
     cudaStream_t stream = nullptr;
     DevBuf in, out, in_off, out_off, out_len, status, detail, cs, dense, dense_off;
-    PinBuf h_dense_off;
+    PinBuf stage;  // pinned staging of the chunk's small arrays (ChunkStage)
     void release() {
         for (DevBuf* b : {&in, &out, &in_off, &out_off, &out_len, &status, &detail, &cs, &dense, &dense_off})
             b->release();
-        h_dense_off.release();
+        stage.release();
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }
@@ -129,7 +132,8 @@ struct slzw_ctx {
     // chunk of streams, the kernels of the previous chunk and the D2H copy of the one before
     // overlap (PCIe is full duplex)
     HostSlot pipe[kPipe];
-    uint64_t chunk_bytes = kChunkBytes;
+    uint64_t enc_chunk_bytes = kEncChunkBytes;
+    uint64_t dec_chunk_bytes = kDecChunkBytes;
     uint64_t launches = 0;
     int last_decode_ws = -1;  // workspace of the most recent decode call
     char err[256] = {0};
@@ -287,9 +291,30 @@ std::vector<uint64_t> chunk_bounds(const uint64_t* weight, uint64_t n, uint64_t 
     return cb;
 }
 
+// Small per-chunk arrays (offsets in, sizes / statuses out) are staged through pinned memory of
+// the pipeline slot: a cudaMemcpyAsync from or to pageable memory blocks the host until the
+// stream reaches it, which would serialise the pipeline.
+struct ChunkStage {
+    uint64_t* in_off;    // m + 1
+    uint64_t* out_off;   // m + 1
+    uint64_t* out_len;   // m   (dense encode: dense_off, m + 1)
+    uint32_t* status;    // m
+    uint32_t* detail;    // m
+    uint8_t* cs;         // m
+    static size_t bytes(uint64_t m) { return 8 * (m + 1) * 3 + 4 * m * 2 + m + 64; }
+    void bind(void* p, uint64_t m) {
+        in_off = (uint64_t*)p;
+        out_off = in_off + (m + 1);
+        out_len = out_off + (m + 1);
+        status = (uint32_t*)(out_len + (m + 1));
+        detail = status + m;
+        cs = (uint8_t*)(detail + m);
+    }
+};
+
 // Host path: the batch goes through the device in chunks of streams, pipelined over kPipe
 // slots (H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 overlap), results land in the
-// caller's buffers.  Pinned host buffers (slzw_host_alloc) make the copies asynchronous.
+// caller's buffers.  Pinned host buffers (slzw_host_alloc) make the large copies asynchronous.
 int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op op) {
     if (!ctx) return SLZW_RC_INVALID;
     if (!params_ok(params) || !b) {
@@ -308,8 +333,11 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
     // chunk by the larger side of the stream (uncompressed bytes)
     const std::vector<uint64_t> cb =
-        chunk_bounds(needs_out && op == Op::Decode ? b->out_off : b->in_off, n, ctx->chunk_bytes);
-    for (size_t k = 0; k + 1 < cb.size(); k++) {
+        chunk_bounds(needs_out && op == Op::Decode ? b->out_off : b->in_off, n,
+                     op == Op::Encode ? ctx->enc_chunk_bytes : ctx->dec_chunk_bytes);
+    const size_t chunks = cb.size() - 1;
+
+    auto enqueue = [&](size_t k) -> int {
         HostSlot& hs = ctx->pipe[k % kPipe];
         cudaStream_t s = hs.stream;
         const uint64_t s0 = cb[k], s1 = cb[k + 1], m = s1 - s0;
@@ -325,17 +353,22 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
             CK(hs.status.reserve(sizeof(uint32_t) * m), "cudaMalloc(status)");
             CK(hs.detail.reserve(sizeof(uint32_t) * m), "cudaMalloc(detail)");
             if (b->code_size) CK(hs.cs.reserve(m), "cudaMalloc(code_size)");
+            CK(hs.stage.reserve(ChunkStage::bytes(m)), "cudaHostAlloc(stage)");
         }
+        ChunkStage st;
+        st.bind(hs.stage.p, m);
+        memcpy(st.in_off, b->in_off + s0, sizeof(uint64_t) * (m + 1));
+        if (needs_out) memcpy(st.out_off, b->out_off + s0, sizeof(uint64_t) * (m + 1));
+        if (b->code_size) memcpy(st.cs, b->code_size + s0, m);
         // Offsets stay absolute: the device copies of in/out are biased by -lo instead.
         if (in_hi > in_lo)
             CK(cudaMemcpyAsync(hs.in.p, b->in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
-        CK(cudaMemcpyAsync(hs.in_off.p, b->in_off + s0, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
+        CK(cudaMemcpyAsync(hs.in_off.p, st.in_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
            "H2D in_off");
         if (needs_out)
-            CK(cudaMemcpyAsync(hs.out_off.p, b->out_off + s0, sizeof(uint64_t) * (m + 1),
-                               cudaMemcpyHostToDevice, s), "H2D out_off");
-        if (b->code_size)
-            CK(cudaMemcpyAsync(hs.cs.p, b->code_size + s0, m, cudaMemcpyHostToDevice, s), "H2D code_size");
+            CK(cudaMemcpyAsync(hs.out_off.p, st.out_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
+               "H2D out_off");
+        if (b->code_size) CK(cudaMemcpyAsync(hs.cs.p, st.cs, m, cudaMemcpyHostToDevice, s), "H2D code_size");
         slzw_batch d = {};
         d.in = (const uint8_t*)hs.in.p - in_lo;
         d.in_off = (const uint64_t*)hs.in_off.p;
@@ -350,14 +383,31 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
         if (rc != SLZW_RC_OK) return rc;
         if (needs_out && out_hi > out_lo)
             CK(cudaMemcpyAsync(b->out + out_lo, hs.out.p, out_hi - out_lo, cudaMemcpyDeviceToHost, s), "D2H out");
-        CK(cudaMemcpyAsync(b->out_len + s0, hs.out_len.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, s),
-           "D2H out_len");
-        CK(cudaMemcpyAsync(b->status + s0, hs.status.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s),
-           "D2H status");
-        CK(cudaMemcpyAsync(b->detail + s0, hs.detail.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s),
-           "D2H detail");
+        CK(cudaMemcpyAsync(st.out_len, hs.out_len.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, s), "D2H out_len");
+        CK(cudaMemcpyAsync(st.status, hs.status.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H status");
+        CK(cudaMemcpyAsync(st.detail, hs.detail.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H detail");
+        return SLZW_RC_OK;
+    };
+    auto finalize = [&](size_t k) -> int {
+        HostSlot& hs = ctx->pipe[k % kPipe];
+        CK(cudaStreamSynchronize(hs.stream), "cudaStreamSynchronize");
+        const uint64_t s0 = cb[k], m = cb[k + 1] - cb[k];
+        ChunkStage st;
+        st.bind(hs.stage.p, m);
+        memcpy(b->out_len + s0, st.out_len, sizeof(uint64_t) * m);
+        memcpy(b->status + s0, st.status, sizeof(uint32_t) * m);
+        memcpy(b->detail + s0, st.detail, sizeof(uint32_t) * m);
+        return SLZW_RC_OK;
+    };
+
+    int rc;
+    for (size_t k = 0; k < chunks; k++) {
+        if ((rc = enqueue(k)) != SLZW_RC_OK) return rc;
+        // the slot chunk k+1 will use is the one of chunk k+1-kPipe: finish that chunk now
+        if (k + 1 >= (size_t)kPipe && (rc = finalize(k + 1 - kPipe)) != SLZW_RC_OK) return rc;
     }
-    for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->pipe[i].stream), "cudaStreamSynchronize");
+    for (size_t k = chunks >= (size_t)kPipe ? chunks - kPipe + 1 : 0; k < chunks; k++)
+        if ((rc = finalize(k)) != SLZW_RC_OK) return rc;
     return SLZW_RC_OK;
 }
 
@@ -380,27 +430,36 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     if (align == 0) align = 1;
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
-    // worst-case slots, 16-byte aligned so that the packer's word stores are aligned
-    std::vector<uint64_t> slots(n + 1);
-    slots[0] = 0;
-    for (uint64_t i = 0; i < n; i++) {
-        const uint64_t bnd = slzw_encode_bound(params, in_off[i + 1] - in_off[i]);
-        slots[i + 1] = slots[i] + ((bnd + 15) & ~15ull);
-    }
-    const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->chunk_bytes);
+    const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->enc_chunk_bytes);
     const size_t chunks = cb.size() - 1;
+    uint64_t hbase = 0;  // dense bytes placed so far
+    bool overflow = false;
 
     auto enqueue = [&](size_t k) -> int {
         HostSlot& hs = ctx->pipe[k % kPipe];
         cudaStream_t s = hs.stream;
         const uint64_t s0 = cb[k], s1 = cb[k + 1], m = s1 - s0;
         const uint64_t in_lo = in_off[s0], in_hi = in_off[s1];
-        const uint64_t sl_lo = slots[s0], sl_hi = slots[s1];
+        {
+            std::lock_guard<std::mutex> lock(ctx->mu);
+            CK(hs.stage.reserve(ChunkStage::bytes(m)), "cudaHostAlloc(stage)");
+        }
+        ChunkStage st;
+        st.bind(hs.stage.p, m);
+        // worst-case slots of the chunk, 16-byte aligned so that the packer's word stores are aligned
+        st.out_off[0] = 0;
+        for (uint64_t i = 0; i < m; i++) {
+            const uint64_t bnd = slzw_encode_bound(params, in_off[s0 + i + 1] - in_off[s0 + i]);
+            st.out_off[i + 1] = st.out_off[i] + ((bnd + 15) & ~15ull);
+        }
+        const uint64_t slot_bytes = st.out_off[m];
+        memcpy(st.in_off, in_off + s0, sizeof(uint64_t) * (m + 1));
+        if (code_size) memcpy(st.cs, code_size + s0, m);
         {
             std::lock_guard<std::mutex> lock(ctx->mu);
             CK(hs.in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
-            CK(hs.out.reserve(sl_hi - sl_lo + 16), "cudaMalloc(slots)");
-            CK(hs.dense.reserve(sl_hi - sl_lo + align * m + 16), "cudaMalloc(dense)");
+            CK(hs.out.reserve(slot_bytes + 16), "cudaMalloc(slots)");
+            CK(hs.dense.reserve(slot_bytes + align * m + 16), "cudaMalloc(dense)");
             CK(hs.in_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(in_off)");
             CK(hs.out_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(out_off)");
             CK(hs.dense_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(dense_off)");
@@ -408,19 +467,18 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
             CK(hs.status.reserve(sizeof(uint32_t) * m), "cudaMalloc(status)");
             CK(hs.detail.reserve(sizeof(uint32_t) * m), "cudaMalloc(detail)");
             if (code_size) CK(hs.cs.reserve(m), "cudaMalloc(code_size)");
-            CK(hs.h_dense_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaHostAlloc(dense_off)");
         }
         if (in_hi > in_lo)
             CK(cudaMemcpyAsync(hs.in.p, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
-        CK(cudaMemcpyAsync(hs.in_off.p, in_off + s0, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
+        CK(cudaMemcpyAsync(hs.in_off.p, st.in_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
            "H2D in_off");
-        CK(cudaMemcpyAsync(hs.out_off.p, slots.data() + s0, sizeof(uint64_t) * (m + 1),
-                           cudaMemcpyHostToDevice, s), "H2D slots");
-        if (code_size) CK(cudaMemcpyAsync(hs.cs.p, code_size + s0, m, cudaMemcpyHostToDevice, s), "H2D code_size");
+        CK(cudaMemcpyAsync(hs.out_off.p, st.out_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
+           "H2D slots");
+        if (code_size) CK(cudaMemcpyAsync(hs.cs.p, st.cs, m, cudaMemcpyHostToDevice, s), "H2D code_size");
         slzw_batch d = {};
         d.in = (const uint8_t*)hs.in.p - in_lo;
         d.in_off = (const uint64_t*)hs.in_off.p;
-        d.out = (uint8_t*)hs.out.p - sl_lo;
+        d.out = (uint8_t*)hs.out.p;
         d.out_off = (const uint64_t*)hs.out_off.p;
         d.out_len = (uint64_t*)hs.out_len.p;
         d.status = (uint32_t*)hs.status.p;
@@ -432,31 +490,41 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         CK(compact_launch(d.out, d.out_off, d.out_len, m, align, (uint8_t*)hs.dense.p,
                           (uint64_t*)hs.dense_off.p, ctx->num_sms, s), "compaction launch");
         ctx->launches += 2;
-        CK(cudaMemcpyAsync(hs.h_dense_off.p, hs.dense_off.p, sizeof(uint64_t) * (m + 1),
-                           cudaMemcpyDeviceToHost, s), "D2H dense_off");
-        CK(cudaMemcpyAsync(status + s0, hs.status.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H status");
-        CK(cudaMemcpyAsync(detail + s0, hs.detail.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H detail");
+        // the chunk's dense offsets come back in the out_len area of the stage (m + 1 entries)
+        CK(cudaMemcpyAsync(st.out_len, hs.dense_off.p, sizeof(uint64_t) * (m + 1), cudaMemcpyDeviceToHost, s),
+           "D2H dense_off");
+        CK(cudaMemcpyAsync(st.status, hs.status.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H status");
+        CK(cudaMemcpyAsync(st.detail, hs.detail.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H detail");
         return SLZW_RC_OK;
     };
-
-    uint64_t hbase = 0;  // dense bytes placed so far
-    bool overflow = false;
-    int rc = enqueue(0);
-    if (rc != SLZW_RC_OK) return rc;
-    for (size_t k = 0; k < chunks; k++) {
-        if (k + 1 < chunks && (rc = enqueue(k + 1)) != SLZW_RC_OK) return rc;
+    // chunk k's kernels are done: place it behind chunk k-1 and start the copy of its bytes
+    auto place = [&](size_t k) -> int {
         HostSlot& hs = ctx->pipe[k % kPipe];
         CK(cudaStreamSynchronize(hs.stream), "cudaStreamSynchronize");
         const uint64_t s0 = cb[k], m = cb[k + 1] - cb[k];
-        const uint64_t* rel = (const uint64_t*)hs.h_dense_off.p;
-        const uint64_t total = rel[m];
-        for (uint64_t i = 1; i <= m; i++) out_off[s0 + i] = hbase + rel[i];
+        ChunkStage st;
+        st.bind(hs.stage.p, m);
+        const uint64_t total = st.out_len[m];
+        for (uint64_t i = 1; i <= m; i++) out_off[s0 + i] = hbase + st.out_len[i];
+        memcpy(status + s0, st.status, sizeof(uint32_t) * m);
+        memcpy(detail + s0, st.detail, sizeof(uint32_t) * m);
         if (hbase + total > out_cap) overflow = true;
         if (!overflow && total)
             CK(cudaMemcpyAsync(out_dense + hbase, hs.dense.p, total, cudaMemcpyDeviceToHost, hs.stream),
                "D2H dense");
         hbase += total;
+        return SLZW_RC_OK;
+    };
+
+    int rc;
+    for (size_t k = 0; k < chunks; k++) {
+        if ((rc = enqueue(k)) != SLZW_RC_OK) return rc;
+        // chunks are placed in order, one chunk behind the newest launch; the slot chunk k+1 will
+        // use (that of chunk k+1-kPipe) has been placed by then and its copy is ordered before
+        // the reuse by the slot's stream
+        if (k >= 1 && (rc = place(k - 1)) != SLZW_RC_OK) return rc;
     }
+    if ((rc = place(chunks - 1)) != SLZW_RC_OK) return rc;
     for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->pipe[i].stream), "cudaStreamSynchronize");
     if (needed) *needed = hbase;
     if (overflow) {
@@ -513,7 +581,7 @@ int slzw_create(int device, slzw_ctx** out) {
     if (const char* e = getenv("SLZW_ENC_CONFIG")) encode_select_config(atoi(e));  // tuning knob
     if (const char* e = getenv("SLZW_HOST_CHUNK_BYTES")) {
         const long long v = atoll(e);  // tests use tiny chunks
-        if (v > 0) ctx->chunk_bytes = (uint64_t)v;
+        if (v > 0) ctx->enc_chunk_bytes = ctx->dec_chunk_bytes = (uint64_t)v;
     }
     DeviceGuard guard(device);
     if (!guard.ok || encode_configure() != cudaSuccess || decode_exact_configure() != cudaSuccess ||
