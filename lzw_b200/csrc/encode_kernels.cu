@@ -1,25 +1,30 @@
 // encode_kernels.cu -- batched LZW encoder for sm_100a.
 //
-// One warp per stream, one persistent CTA of 12 or 13 warps per SM, streams handed out through a
-// global work queue in the order chosen by the scheduler.  Every warp owns one 16 KB dictionary that
-// is 16 KB-ALIGNED in the shared-memory window, so that `table base | slot offset` needs no add:
-// the base is folded into the per-byte hash bits and a probe address is one LOP3 away from the
-// slot word it depends on.  Per stream:
-//   * the reference's arena trie (encoder.rs:58-149) is replaced by an open-addressing hash
-//     dictionary keyed on (prefix code, next byte) -> code, one u32 per slot
-//     [prefix':12 | byte:8 | code':12], 4096 slots = 16 KB of shared memory.  x' = x * 0x9E5 mod 4096
-//     is a bijection of the 12-bit codes ("scrambled" codes); the slot index is
-//     prefix' ^ (byte * 0x6A7 mod 4096), so the next probe address is a shift and one LOP3 away from
-//     the slot word that was just loaded.  Numbering of new entries is insertion order and lookups
-//     are exact (full linear probing), so the emitted codes equal the reference's;
-//   * the match loop (encoder.rs:313-337) is a dependent chain, one probe per input byte.  It is
-//     executed by all 32 lanes with identical values (no divergence); the probe for byte i+1 is
-//     issued speculatively (assuming byte i hits) before byte i's key comparison resolves, so a
-//     run of hits costs LDS -> SHF -> LOP3 -> LDS per byte;
-//   * everything about an input byte that does not depend on the chain (key bits, hash bits) is
-//     precomputed by the whole warp into a 64-bit record per byte (the input tile never sits in
-//     shared memory as raw bytes; the next tile's words are prefetched into registers while the
-//     current tile is matched);
+// One warp per stream, one persistent CTA of 28 warps per SM, streams handed out through a global
+// work queue in the order chosen by the scheduler.  What limits the number of streams in flight is
+// room for their dictionaries (the reference's arena trie, encoder.rs:58-149, becomes an
+// open-addressing hash dictionary keyed on (prefix code, next byte) -> code, one u32 per slot
+// [prefix':12 | byte:8 | code':12], 4096 slots = 16 KB):
+//   * warps 16..27 keep theirs in shared memory (12 x 16 KB, 16 KB-aligned in the shared window so
+//     that `base | offset` needs no add);
+//   * warps 0..15 keep theirs in TENSOR MEMORY, which a codec otherwise never touches: 16 x 128
+//     columns of the SM's 512, accessed with tcgen05.ld / tcgen05.st (32x32b shapes).
+// x' = x * 0x9E5 mod 4096 is a bijection of the 12-bit codes ("scrambled" codes): dense sequential
+// codes would form runs under an XOR hash, scrambled ones do not, and prefix' ^ hash(byte) then
+// collides no more often than a 32-bit multiplicative hash of the whole key (measured,
+// profiles/r01_encode_notes.md).  Numbering of new entries is insertion order and lookups are
+// exact (probing never gives up), so the emitted codes equal the reference's.
+//
+// Per stream:
+//   * the match loop (encoder.rs:313-337) is a dependent chain, one dictionary lookup per input
+//     byte, executed by all 32 lanes with warp-uniform control flow.  Default: bucket lookups
+//     (match_tile_bucket: one load, one ballot, one shuffle per byte); alternative for shared
+//     memory: scalar probes with a speculative next probe and a 32-wide collision window
+//     (match_tile);
+//   * everything about an input byte that does not depend on the chain (key bits, hash bits,
+//     dictionary base) is precomputed by the whole warp into a 64-bit record per byte; the input
+//     never sits in shared memory as raw bytes, and the next tile's words are prefetched into
+//     registers while the current tile is matched;
 //   * emitted codes are buffered as [width:4 | code':12] and bit-packed by the whole warp
 //     (LSB-first like io.rs:234-248 or MSB-first like io.rs:296-311) into a shared-memory word
 //     window that is written to the output slot with aligned 32-bit stores;
@@ -33,15 +38,9 @@ namespace slzw {
 
 namespace {
 
-// Wide handling of miss runs (see match_tile).  Exact, but measured slower on the B200 with linear
-// probing at a load factor of up to 0.94: the longest private probe sequence of the 32 lanes sets
-// the pace (66 slots on average for random bytes), 21.2 ms vs 15.9 ms for 151 MB of random
-// strips and 31.1 ms vs 14.9 ms for photo-like strips (profiles/r01_encode_notes.md).  Kept
-// behind this switch for the next round (bounded probing / double hashing).
-constexpr bool kWideMissRuns = false;
-
 constexpr int kSlots = 4096;
 constexpr uint32_t kIdxMask4 = (uint32_t)(kSlots - 1) << 2;  // byte offset of a slot
+constexpr uint32_t kBucketMask = 127u << 7;                   // byte offset of a 32-slot bucket
 constexpr uint32_t kScr = 0x9E5u;     // code -> code' = code * kScr mod 4096 (odd => bijection)
 constexpr uint32_t kScrInv = 0xBEDu;  // kScr * kScrInv == 1 mod 4096
 constexpr uint32_t kByteMul = 0x6A7u; // byte -> hash contribution
@@ -131,6 +130,13 @@ __device__ __forceinline__ bool probe_wide(uint32_t tb, uint32_t key, int lane, 
     return false;
 }
 
+// index of the most significant set bit (FLO)
+__device__ __forceinline__ uint32_t bfind(uint32_t v) {
+    uint32_t r;
+    asm("bfind.u32 %0, %1;\n" : "=r"(r) : "r"(v));
+    return r;
+}
+
 __device__ __forceinline__ void clear_table(uint32_t* table, int lane) {
 #pragma unroll 4
     for (int j = lane; j < kSlots / 4; j += kWarpSize)
@@ -142,16 +148,6 @@ __device__ __forceinline__ void clear_table(uint32_t* table, int lane) {
 // The loop never leaves the tile early: input validation truncates the tile beforehand and the
 // capacity check happens per tile (see encode_stream).
 //
-// Two modes, both exact:
-//   * scalar: every lane executes the same dependent chain, one probe per byte, with the probe
-//     of byte i+1 issued speculatively before byte i's comparison resolves (runs of hits);
-//   * wide: after two consecutive misses the current prefix is a single byte, and as long as the
-//     misses go on so is every following prefix -- the keys (byte i-1, byte i) do not depend on
-//     the chain.  Lane j then looks up the key of byte i+j on its own (private linear probing).
-//     Sequentially, byte i+j is a miss that inserts into the empty slot lane j found iff every
-//     earlier lane is a miss too and none of them claimed the same slot (an earlier insert can
-//     only change lane j's lookup by filling exactly that slot, which also covers equal keys).
-//     The warp commits the longest such prefix of lanes at once: codes, inserts, counters.
 template <bool FIXED, int U>
 __device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const uint32_t tb,
                                            const uint2* __restrict__ rec,
@@ -166,7 +162,6 @@ __device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const u
     uint32_t mask = m.mask;
     uint32_t until = m.until;
     uint32_t cp = m.ncodes;
-    uint32_t lastmiss = 0xFFFFFFF0u;  // tile index of the most recent miss
     uint32_t i = 0;
     uint2 r0;
     uint32_t a, s;
@@ -193,10 +188,10 @@ __device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const u
         }                                                                                       \
     }
 
-    // One byte of encoder.rs:313-337.  RC = record of this byte (tile index i + OFF), RN = record
+    // One byte of encoder.rs:313-337.  RC = record of this byte, RN = record
     // of the next byte (anything addressable when this is the last byte of the tile: the
     // lookahead is discarded).  On entry `s` is the word of the home slot `a` of the key (t, RC).
-#define SLZW_STEP(RC, RN, OFF)                                                                  \
+#define SLZW_STEP(RC, RN)                                                                       \
     {                                                                                           \
         const uint32_t an = ((s << 2) & kIdxMask4) ^ (RN).y;                                    \
         const uint32_t sn = tbl_ld(an);    /* speculative: assumes this byte hits */            \
@@ -221,39 +216,31 @@ __device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const u
                     if (!FIXED && until == 0u) SLZW_BUMP()                                      \
                 }                                                                               \
                 t = (RC).x * (kScr << 8); /* prefix = this byte: (k * kScr mod 4096) << 20 */   \
-                if (kWideMissRuns && lastmiss + 1u == i + (OFF) && i + (OFF) + 1u < len) {      \
-                    i += (OFF) + 1u;                                                            \
-                    goto wide;                                                                  \
-                }                                                                               \
-                lastmiss = i + (OFF);                                                           \
             }                                                                                   \
             a = ((t >> 18) & kIdxMask4) ^ (RN).y;                                               \
             s = tbl_ld(a);                                                                      \
         }                                                                                       \
     }
 
-restart:
-    if (i >= len) goto done;
-    r0 = rec[i];
-    a = (t >> 18) ^ r0.y;  // home slot of (prefix, byte i); t >> 18 == prefix' << 2
+    r0 = rec[0];
+    a = (t >> 18) ^ r0.y;  // home slot of (prefix, byte 0); t >> 18 == prefix' << 2
     s = tbl_ld(a);
-    // U = unrolling of the step: 4 saves loop overhead, 1 keeps the hot code small (28 warps of
-    // two kernel variants share the SM's instruction caches)
+    // U = unrolling of the step (loop overhead against instruction-cache footprint)
     if constexpr (U >= 4) {
         while (i + 4u <= len) {
             const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
-            SLZW_STEP(r0, r1, 0u)
-            SLZW_STEP(r1, r2, 1u)
-            SLZW_STEP(r2, r3, 2u)
-            SLZW_STEP(r3, r4, 3u)
+            SLZW_STEP(r0, r1)
+            SLZW_STEP(r1, r2)
+            SLZW_STEP(r2, r3)
+            SLZW_STEP(r3, r4)
             r0 = r4;
             i += 4u;
         }
     } else if constexpr (U >= 2) {
         while (i + 2u <= len) {
             const uint2 r1 = rec[i + 1], r2 = rec[i + 2];
-            SLZW_STEP(r0, r1, 0u)
-            SLZW_STEP(r1, r2, 1u)
+            SLZW_STEP(r0, r1)
+            SLZW_STEP(r1, r2)
             r0 = r2;
             i += 2u;
         }
@@ -261,68 +248,10 @@ restart:
 #pragma unroll 1
     while (i < len) {
         const uint2 r1 = rec[i + 1];
-        SLZW_STEP(r0, r1, 0u)
+        SLZW_STEP(r0, r1)
         r0 = r1;
         i += 1u;
     }
-    goto done;
-
-wide: {
-        // bytes i .. i+L-1, lane j owns byte i+j; its prefix is byte i+j-1 (lane 0: t)
-        const bool inserting = !FIXED || until != 0u;
-        uint32_t L = len - i < (uint32_t)kWarpSize ? len - i : (uint32_t)kWarpSize;
-        if (inserting && until < L) L = until;
-        const bool on = (uint32_t)lane < L;
-        const uint32_t idx = on ? i + (uint32_t)lane : i;
-        const uint2 rc = rec[idx];
-        uint32_t tj = t;
-        if (on && lane > 0) tj = rec[idx - 1u].x * (kScr << 8);
-        const uint32_t key = tj | rc.x;
-        uint32_t al = (tj >> 18) ^ rc.y;
-        bool found = false;
-        if (on) {
-            for (int guard = 0; guard < kSlots; guard++) {  // private linear probing
-                const uint32_t v = tbl_ld(al);
-                if (v == 0u) break;
-                if (((v ^ key) >> 12) == 0u) {
-                    found = true;
-                    break;
-                }
-                al = tb | ((al + 4u) & kIdxMask4);
-            }
-        }
-        const uint32_t hm = __ballot_sync(kFullMask, on && found);
-        uint32_t cnt = hm ? (uint32_t)__ffs(hm) - 1u : L;  // lanes in front of the first hit
-        if (inserting) {
-            // two lanes that claim the same empty slot: the later one has to look again
-            const uint32_t peers =
-                __match_any_sync(kFullMask, (uint32_t)lane < cnt ? al : (0x80000000u | (uint32_t)lane));
-            const uint32_t cm = __ballot_sync(kFullMask, (uint32_t)lane < cnt &&
-                                                             (peers & ((1u << lane) - 1u)) != 0u);
-            if (cm) cnt = (uint32_t)__ffs(cm) - 1u;
-        }
-        if ((uint32_t)lane < cnt) {
-            codes[cp + (uint32_t)lane] = (uint16_t)((tj >> 20) | wtag);
-            if (inserting) tbl_st(al, key | ((ncs + (uint32_t)lane * kScr) & 0xFFFu));
-        }
-        __syncwarp();
-        if (cnt) {
-            cp += cnt;
-            t = rec[i + cnt - 1u].x * (kScr << 8);
-            i += cnt;
-            lastmiss = i - 1u;
-            if (inserting) {
-                ncs = (ncs + cnt * kScr) & 0xFFFu;
-                until -= cnt;
-                if (!FIXED && until == 0u) SLZW_BUMP()
-            }
-        } else {
-            lastmiss = 0xFFFFFFF0u;  // byte i hits: back to the chain
-        }
-        goto restart;
-    }
-
-done:
 #undef SLZW_STEP
 #undef SLZW_BUMP
     m.t = t;
@@ -337,11 +266,9 @@ done:
 // Shared memory holds twelve 16 KB dictionaries per SM and nothing else limits the number of
 // streams in flight.  The SM's 256 KB of tensor memory (512 columns x 128 lanes x 32 bit) is idle
 // in this kernel, so sixteen more warps keep their dictionary there: warp w owns the 32 lanes of
-// its lane quarter (w % 4, the only ones a warp can address) and 128 columns, one column = 32
-// slots.  A probe is `tcgen05.ld.32x32b.x1` of the slot's column (every lane receives its lane's
-// word) plus a shuffle from the slot's lane; the words of the column double as the collision
-// window (the probe sequence is the home slot, then the rest of its column in lane order, then
-// the following columns), and an insert stores the column back with one lane's word replaced.
+// its lane quarter (w % 4, the only ones a warp can address) and 128 columns; one column = one
+// 32-slot bucket, `tcgen05.ld.32x32b.x1` hands every lane its slot of the bucket, and an insert
+// stores the column back with one lane's word replaced (`tcgen05.st`).
 __device__ __forceinline__ uint32_t tmem_ld(uint32_t taddr) {
     uint32_t v;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n" : "=r"(v) : "r"(taddr));
@@ -369,136 +296,132 @@ __device__ __forceinline__ void tmem_clear(uint32_t tbase) {
     tmem_wait_st();
 }
 
-// match_tile for a dictionary in tensor memory.  rec[i] = {byte << 12, dictionary's tensor-memory
-// address | 7 hash bits of the byte}: the column of the key (prefix, byte) is
-// (prefix' & 127) ^ hash7(byte), its lane is prefix' >> 7.  Same speculative structure as the
-// shared-memory loop: the column of byte i+1 is requested (assuming byte i hits) before byte i's
-// comparison resolves.
-template <bool FIXED, int U>
-__device__ __forceinline__ void match_tile_tmem(const uint32_t tbase, const uint2* __restrict__ rec,
-                                                uint16_t* __restrict__ codes, const int lane,
-                                                const uint32_t len, MatchState& m,
-                                                const uint32_t cs, const uint32_t inc,
-                                                const uint32_t clear_code,
-                                                const uint32_t first_code) {
-    uint32_t t = m.t;
+// ---- bucket variant of the match loop -----------------------------------------------------------
+// With 28 warps per SM the encoder is bound by instruction issue, not by the latency of the
+// dependent chain (profiles/r01b_bench_encode_ncu_summary.txt: issue slots 87 % busy), so the
+// variant with the fewest instructions per input byte wins, whatever its chain length.  Here the
+// dictionary is 128 buckets of 32 slots: a bucket is one 128-byte line of shared memory or one
+// column of tensor memory, lane l owns slot l of every bucket, and every lookup is ONE load in
+// which each lane reads its slot of the key's bucket, one ballot over "my slot holds this key" and
+// one shuffle of the matching slot's code.  A bucket fills from slot 0 upwards; a key that is not
+// in its bucket while the bucket still has an empty slot is not in the dictionary (miss: the lane
+// that owns the first empty slot inserts it); a full bucket overflows into the next one.  There is
+// no separate collision path and no speculation: 1.00 to 1.14 bucket loads per input byte on the
+// config-3 strips at the format's load factor of up to 0.94 (profiles/r01_encode_notes.md).
+// rec[i] = {byte << 12, hash7(byte) << 7} (shared memory) or {byte << 12, dictionary's
+// tensor-memory address | hash7(byte)} (tensor memory); `tl` = shared address of this lane's slot
+// in bucket 0, `tb` = tensor-memory address of the dictionary.
+template <bool FIXED, bool TMEM, int U>
+__device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, const uint32_t tl,
+                                                  const uint32_t tb, const uint2* __restrict__ rec,
+                                                  uint16_t* __restrict__ codes, const int lane,
+                                                  const uint32_t len, MatchState& m,
+                                                  const uint32_t cs, const uint32_t inc,
+                                                  const uint32_t clear_code,
+                                                  const uint32_t first_code) {
+    uint32_t t = m.t;                             // prefix' << 20: key position
+    uint32_t tp = TMEM ? m.t >> 20 : m.t >> 13;   // prefix' (column) / prefix' << 7 (bucket offset)
     uint32_t ncs = m.ncs;
     uint32_t ws = FIXED ? 12u : m.ws;
     uint32_t wtag = ws << 12;
     uint32_t mask = m.mask;
     uint32_t until = m.until;
     uint32_t cp = m.ncodes;
+    const uint32_t lanebit = 1u << lane;
 
-    uint2 r0 = rec[0];
-    uint32_t a = ((t >> 20) & 0x7Fu) ^ r0.y;  // column of (prefix, byte 0)
-    uint32_t hl = t >> 27;                    // its lane
-    uint32_t cl = tmem_ld(a);                 // this lane's word of that column
-    tmem_wait_ld(cl);
-    uint32_t s = __shfl_sync(kFullMask, cl, hl);
-
-#define SLZW_STEP_T(RC, RN)                                                                     \
+#define SLZW_STEP_B(RC)                                                                         \
     {                                                                                           \
-        const uint32_t an = (s & 0x7Fu) ^ (RN).y;                                               \
-        uint32_t cn = tmem_ld(an);         /* speculative: assumes this byte hits */            \
-        const uint32_t x = s ^ t ^ (RC).x; /* == code' iff the slot holds this key */           \
-        tmem_wait_ld(cn);                                                                       \
-        if (x - 1u < 4095u) {              /* find_word hit, encoder.rs:319-320 */              \
-            t = s << 20;                                                                        \
-            hl = (s >> 7) & 31u;                                                                \
-            a = an;                                                                             \
-            cl = cn;                                                                            \
-            s = __shfl_sync(kFullMask, cn, hl);                                                 \
-        } else {                                                                                \
-            const uint32_t key = t | (RC).x;                                                    \
-            bool hit = false;                                                                   \
-            uint32_t pos = hl;                                                                  \
-            if (s != 0u) { /* another key at home: the column, then the following columns */    \
-                uint32_t start = hl;                                                            \
-                _Pragma("unroll 1") for (int round = 0; round < 129; round++) {                 \
-                    const uint32_t mm =                                                         \
-                        __ballot_sync(kFullMask, ((cl ^ key) >> 12) == 0u && cl != 0u);         \
-                    const uint32_t me = __ballot_sync(kFullMask, cl == 0u);                     \
-                    const uint32_t stop = mm | me;                                              \
-                    const uint32_t rot = __funnelshift_r(stop, stop, start);                    \
-                    if (rot) {                                                                  \
-                        pos = (start + (uint32_t)__ffs(rot) - 1u) & 31u;                        \
-                        hit = (mm >> pos) & 1u;                                                 \
-                        break;                                                                  \
-                    }                                                                           \
-                    a = (a & ~0x7Fu) | ((a + 1u) & 0x7Fu);                                      \
-                    start = 0u;                                                                 \
-                    cl = tmem_ld(a);                                                            \
-                    tmem_wait_ld(cl);                                                           \
-                }                                                                               \
-            }                                                                                   \
-            if (hit) {                                                                          \
-                s = __shfl_sync(kFullMask, cl, pos);                                            \
-                t = s << 20;                                                                    \
+        const uint32_t key = t | (RC).x;                                                        \
+        uint32_t a = TMEM ? ((tp & 0x7Fu) ^ (RC).y) : (tl | ((tp ^ (RC).y) & kBucketMask));     \
+        _Pragma("unroll 1") for (;;) {                                                          \
+            uint32_t v;                                                                         \
+            if (TMEM) {                                                                         \
+                v = tmem_ld(a);                                                                 \
+                tmem_wait_ld(v);                                                                \
             } else {                                                                            \
-                /* miss: encoder.rs:322-324 / 645-649 */                                        \
-                codes[cp++] = (uint16_t)((t >> 20) | wtag);                                     \
-                if (!FIXED || until != 0u) {                                                    \
-                    if ((uint32_t)lane == pos) cl = key | ncs;                                  \
-                    tmem_st(a, cl);                                                             \
+                v = tbl_ld(a);                                                                  \
+            }                                                                                   \
+            const uint32_t x = v ^ key; /* == code' iff my slot holds the key */                \
+            const uint32_t bal = __ballot_sync(kFullMask, x - 1u < 4095u);                      \
+            if (bal) { /* find_word hit, encoder.rs:319-320 */                                  \
+                const uint32_t c = __shfl_sync(kFullMask, x, (int)bfind(bal));                  \
+                t = c << 20;                                                                    \
+                tp = TMEM ? c : c << 7;                                                         \
+                break;                                                                          \
+            }                                                                                   \
+            const uint32_t em = __ballot_sync(kFullMask, v == 0u);                              \
+            if (em == 0u) { /* full bucket: the key may have overflowed into the next one */    \
+                a = TMEM ? ((a & ~0x7Fu) | ((a + 1u) & 0x7Fu))                                  \
+                         : ((a & ~kBucketMask) | ((a + 128u) & kBucketMask));                   \
+                continue;                                                                       \
+            }                                                                                   \
+            /* miss: encoder.rs:322-324 / 645-649 */                                            \
+            codes[cp++] = (uint16_t)((t >> 20) | wtag);                                         \
+            if (!FIXED || until != 0u) {                                                        \
+                const bool mine = (em & (0u - em)) == lanebit; /* first empty slot */           \
+                if (TMEM) {                                                                     \
+                    tmem_st(a, mine ? (key | ncs) : v);                                         \
                     tmem_wait_st();                                                             \
-                    ncs = (ncs + kScr) & 0xFFFu;                                                \
-                    until--;                                                                    \
-                    if (!FIXED && until == 0u) { /* new index == mask, encoder.rs:326 */        \
-                        if (ws < 12u) {          /* encoder.rs:327-328 */                       \
-                            ws++;                                                               \
-                            wtag = ws << 12;                                                    \
-                            const uint32_t nm = (1u << ws) - inc;                               \
-                            until = nm - mask;                                                  \
-                            mask = nm;                                                          \
-                        } else { /* encoder.rs:329-333 */                                       \
-                            codes[cp++] = (uint16_t)(scr(clear_code) | (12u << 12));            \
-                            ws = cs + 1u;                                                       \
-                            wtag = ws << 12;                                                    \
-                            mask = (1u << ws) - inc;                                            \
-                            until = mask - first_code + 1u;                                     \
-                            ncs = scr(first_code);                                              \
-                            tmem_clear(tbase);                                                  \
+                } else {                                                                        \
+                    if (mine) tbl_st(a, key | ncs);                                             \
+                }                                                                               \
+                ncs = (ncs + kScr) & 0xFFFu;                                                    \
+                until--;                                                                        \
+                if (!FIXED && until == 0u) { /* new index == mask, encoder.rs:326 */            \
+                    if (ws < 12u) {          /* encoder.rs:327-328 */                           \
+                        ws++;                                                                   \
+                        wtag = ws << 12;                                                        \
+                        const uint32_t nm = (1u << ws) - inc;                                   \
+                        until = nm - mask;                                                      \
+                        mask = nm;                                                              \
+                    } else { /* encoder.rs:329-333: clear at 12 bits, dictionary restarts */    \
+                        codes[cp++] = (uint16_t)(scr(clear_code) | (12u << 12));                \
+                        ws = cs + 1u;                                                           \
+                        wtag = ws << 12;                                                        \
+                        mask = (1u << ws) - inc;                                                \
+                        until = mask - first_code + 1u;                                         \
+                        ncs = scr(first_code);                                                  \
+                        if (TMEM) {                                                             \
+                            tmem_clear(tb);                                                     \
+                        } else {                                                                \
+                            __syncwarp();                                                       \
+                            clear_table(table, lane);                                           \
                         }                                                                       \
                     }                                                                           \
                 }                                                                               \
-                t = (RC).x * (kScr << 8); /* prefix = this byte */                              \
+                if (!TMEM) __syncwarp(); /* the new entry is visible to every lane's next load */ \
             }                                                                                   \
-            a = ((t >> 20) & 0x7Fu) ^ (RN).y;                                                   \
-            hl = t >> 27;                                                                       \
-            cl = tmem_ld(a);                                                                    \
-            tmem_wait_ld(cl);                                                                   \
-            s = __shfl_sync(kFullMask, cl, hl);                                                 \
+            t = (RC).x * (kScr << 8); /* prefix = this byte: (k * kScr mod 4096) << 20 */       \
+            tp = TMEM ? t >> 20 : t >> 13;                                                      \
+            break;                                                                              \
         }                                                                                       \
     }
 
     uint32_t i = 0;
     if constexpr (U >= 4) {
         while (i + 4u <= len) {
-            const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
-            SLZW_STEP_T(r0, r1)
-            SLZW_STEP_T(r1, r2)
-            SLZW_STEP_T(r2, r3)
-            SLZW_STEP_T(r3, r4)
-            r0 = r4;
+            const uint2 r0 = rec[i], r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3];
+            SLZW_STEP_B(r0)
+            SLZW_STEP_B(r1)
+            SLZW_STEP_B(r2)
+            SLZW_STEP_B(r3)
             i += 4u;
         }
     } else if constexpr (U >= 2) {
         while (i + 2u <= len) {
-            const uint2 r1 = rec[i + 1], r2 = rec[i + 2];
-            SLZW_STEP_T(r0, r1)
-            SLZW_STEP_T(r1, r2)
-            r0 = r2;
+            const uint2 r0 = rec[i], r1 = rec[i + 1];
+            SLZW_STEP_B(r0)
+            SLZW_STEP_B(r1)
             i += 2u;
         }
     }
 #pragma unroll 1
     while (i < len) {
-        const uint2 r1 = rec[i + 1];
-        SLZW_STEP_T(r0, r1)
-        r0 = r1;
+        const uint2 r0 = rec[i];
+        SLZW_STEP_B(r0)
         i += 1u;
     }
-#undef SLZW_STEP_T
+#undef SLZW_STEP_B
 
     m.t = t;
     m.ncs = ncs;
@@ -523,7 +446,7 @@ __device__ __forceinline__ uint32_t load_tile_word(const uint8_t* __restrict__ p
 // unused); otherwise `table` / `tb` are the generic pointer and the shared-window address of its
 // 16 KB.  One function body for both kinds of warp: everything but the match loop is shared, which
 // keeps the instruction footprint of the 28 warps down.
-template <int TILE, bool FIXED, bool HAS_TMEM, int U>
+template <int TILE, bool FIXED, bool HAS_TMEM, int U, bool BS>
 __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restrict__ table,
                               const uint32_t tb, const bool tmem_warp, EncMisc<TILE>& S, int lane) {
     const bool TMEM = HAS_TMEM && tmem_warp;
@@ -667,7 +590,9 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
             const uint32_t idx = 4u * (uint32_t)lane + (uint32_t)b - skew;  // wraps before the tile
             const uint32_t k = (w >> (8 * b)) & 0xFFu;
             if (idx < tile_len) {
-                rec[idx] = make_uint2(k << 12, TMEM ? (tb | (((k * kByteMul) >> 2) & 0x7Fu))
+                const uint32_t h7 = ((k * kByteMul) >> 2) & 0x7Fu;
+                rec[idx] = make_uint2(k << 12, TMEM ? (tb | h7)
+                                               : BS ? (h7 << 7)
                                                     : (tb | (((k * kByteMul) << 2) & kIdxMask4)));
                 if (!FIXED && k > max_code && idx < bad) bad = idx;
             }
@@ -688,7 +613,11 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
 
         if (len) {
             if (TMEM)
-                match_tile_tmem<FIXED, U>(tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
+                match_tile_bucket<FIXED, true, U>(table, 0u, tb, rec, codes, lane, len, m, cs, inc,
+                                                  clear_code, first_code);
+            else if constexpr (BS)
+                match_tile_bucket<FIXED, false, U>(table, tb | (4u * (uint32_t)lane), 0u, rec, codes, lane,
+                                                   len, m, cs, inc, clear_code, first_code);
             else
                 match_tile<FIXED, U>(table, tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
         }
@@ -774,7 +703,7 @@ struct EncLayout {
 
 // Warps [0, TWARPS) keep their dictionary in tensor memory, warps [TWARPS, TWARPS + SWARPS) in
 // shared memory.
-template <int TILE, int SWARPS, int TWARPS, int U, bool FIXED>
+template <int TILE, int SWARPS, int TWARPS, int U, bool BS, bool FIXED>
 __global__ void __launch_bounds__((SWARPS + TWARPS) * kWarpSize, 1)
 slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -818,7 +747,7 @@ slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= a.n) break;
         const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-        encode_stream<TILE, FIXED, (TWARPS > 0), U>(a, sid, table, tb, tmem_warp, S, lane);
+        encode_stream<TILE, FIXED, (TWARPS > 0), U, BS>(a, sid, table, tb, tmem_warp, S, lane);
     }
 
     if constexpr (TWARPS > 0) {
@@ -833,7 +762,7 @@ slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
 
 // ---- launch configuration ---------------------------------------------------------------------
 // {input tile, warps with a shared-memory dictionary, warps with a tensor-memory dictionary}
-template <int TILE, int SWARPS, int TWARPS, int U>
+template <int TILE, int SWARPS, int TWARPS, int U, bool BS>
 struct EncConfig {
     using L = EncLayout<TILE, SWARPS, SWARPS + TWARPS>;
     // the shared window of a CTA starts with 1 KB reserved by the system; taking the larger of
@@ -843,10 +772,10 @@ struct EncConfig {
         return (a > b ? a : b) + L::kHead;
     }
     static cudaError_t configure() {
-        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false>,
+        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, BS, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true>,
+        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, BS, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
     }
     static cudaError_t launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
@@ -854,36 +783,35 @@ struct EncConfig {
         const uint64_t ctas = (a.n + WARPS - 1) / WARPS;
         const int grid = (int)(ctas < (uint64_t)num_sms ? ctas : (uint64_t)num_sms);
         if (a.p.flavour == SLZW_FLAVOUR_FIXED)
-            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, BS, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         else
-            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, BS, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         return cudaGetLastError();
     }
 };
 
-using Enc0 = EncConfig<96, 12, 16, 2>;  // 12 shared-memory + 16 tensor-memory dictionaries per SM
-using Enc1 = EncConfig<128, 12, 0, 4>;  // shared memory only
-using Enc2 = EncConfig<96, 12, 16, 4>;
-using Enc3 = EncConfig<96, 12, 16, 1>;
+// {input tile, shared-memory dictionaries, tensor-memory dictionaries, step unrolling,
+//  bucket lookups in shared memory (tensor memory always uses them)}
+using Enc0 = EncConfig<96, 12, 16, 2, true>;    // default: 28 streams per SM, bucket lookups
+using Enc1 = EncConfig<128, 12, 0, 4, false>;   // shared memory only, scalar speculative probes
+using Enc2 = EncConfig<96, 12, 16, 2, false>;   // scalar probes in shared memory, buckets in TMEM
 
 static int g_enc_config = 0;
 
-void encode_select_config(int c) { g_enc_config = (c >= 0 && c <= 3) ? c : 0; }
+void encode_select_config(int c) { g_enc_config = (c >= 0 && c <= 2) ? c : 0; }
 int encode_streams_per_sm() { return g_enc_config == 1 ? 12 : 28; }
 
 cudaError_t encode_configure() {
     cudaError_t e = Enc0::configure();
     if (e != cudaSuccess) return e;
     if ((e = Enc1::configure()) != cudaSuccess) return e;
-    if ((e = Enc2::configure()) != cudaSuccess) return e;
-    return Enc3::configure();
+    return Enc2::configure();
 }
 
 cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
     switch (g_enc_config) {
         case 1: return Enc1::launch(a, num_sms, stream);
         case 2: return Enc2::launch(a, num_sms, stream);
-        case 3: return Enc3::launch(a, num_sms, stream);
         default: return Enc0::launch(a, num_sms, stream);
     }
 }
