@@ -60,6 +60,10 @@ __device__ __forceinline__ uint32_t tbl_ld(uint32_t saddr) {
 __device__ __forceinline__ void tbl_st(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(saddr), "r"(v));
 }
+// code buffer store by shared-window address (no index arithmetic in the loop)
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;\n" ::"r"(saddr), "h"((uint16_t)v) : "memory");
+}
 
 // Per-warp working set besides the dictionary.
 template <int TILE>
@@ -311,7 +315,15 @@ __device__ __forceinline__ void tmem_clear(uint32_t tbase) {
 // rec[i] = {byte << 12, hash7(byte) << 7} (shared memory) or {byte << 12, dictionary's
 // tensor-memory address | hash7(byte)} (tensor memory); `tl` = shared address of this lane's slot
 // in bucket 0, `tb` = tensor-memory address of the dictionary.
-template <bool FIXED, bool TMEM, int U>
+// MODE says what a miss may have to do in this tile (chosen per tile by the caller from the
+// number of inserts left before the next event):
+//   0  every miss inserts and nothing else can happen (no width bump, no reset, table not
+//      full): no per-miss bookkeeping, codes are stored without a width tag (the packer uses the
+//      tile's width);
+//   1  every miss checks for the width bump / reset (variable) or for the table filling up
+//      (fixed); codes carry their width;
+//   2  fixed flavour, table full: lookups only (encoder.rs:645-647).
+template <bool FIXED, bool TMEM, int U, int MODE>
 __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, const uint32_t tl,
                                                   const uint32_t tb, const uint2* __restrict__ rec,
                                                   uint16_t* __restrict__ codes, const int lane,
@@ -321,12 +333,14 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                                                   const uint32_t first_code) {
     uint32_t t = m.t;                             // prefix' << 20: key position
     uint32_t tp = TMEM ? m.t >> 20 : m.t >> 13;   // prefix' (column) / prefix' << 7 (bucket offset)
-    uint32_t ncs = m.ncs;
+    uint32_t ncs = m.ncs;                         // low 12 bits count, upper bits are garbage
     uint32_t ws = FIXED ? 12u : m.ws;
     uint32_t wtag = ws << 12;
     uint32_t mask = m.mask;
     uint32_t until = m.until;
-    uint32_t cp = m.ncodes;
+    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(codes);
+    uint32_t cpa = cbase + 2u * m.ncodes;         // shared address of the next code
+    const uint32_t cpa0 = cpa;
     const uint32_t lanebit = 1u << lane;
 
 #define SLZW_STEP_B(RC)                                                                         \
@@ -356,36 +370,41 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                 continue;                                                                       \
             }                                                                                   \
             /* miss: encoder.rs:322-324 / 645-649 */                                            \
-            codes[cp++] = (uint16_t)((t >> 20) | wtag);                                         \
-            if (!FIXED || until != 0u) {                                                        \
+            sts_u16(cpa, MODE == 1 ? ((t >> 20) | wtag) : (t >> 20));                           \
+            cpa += 2u;                                                                          \
+            if (MODE == 0 || (MODE == 1 && (!FIXED || until != 0u))) {                          \
                 const bool mine = (em & (0u - em)) == lanebit; /* first empty slot */           \
+                const uint32_t entry = key | (ncs & 0xFFFu);                                    \
                 if (TMEM) {                                                                     \
-                    tmem_st(a, mine ? (key | ncs) : v);                                         \
+                    tmem_st(a, mine ? entry : v);                                               \
                     tmem_wait_st();                                                             \
                 } else {                                                                        \
-                    if (mine) tbl_st(a, key | ncs);                                             \
+                    if (mine) tbl_st(a, entry);                                                 \
                 }                                                                               \
-                ncs = (ncs + kScr) & 0xFFFu;                                                    \
-                until--;                                                                        \
-                if (!FIXED && until == 0u) { /* new index == mask, encoder.rs:326 */            \
-                    if (ws < 12u) {          /* encoder.rs:327-328 */                           \
-                        ws++;                                                                   \
-                        wtag = ws << 12;                                                        \
-                        const uint32_t nm = (1u << ws) - inc;                                   \
-                        until = nm - mask;                                                      \
-                        mask = nm;                                                              \
-                    } else { /* encoder.rs:329-333: clear at 12 bits, dictionary restarts */    \
-                        codes[cp++] = (uint16_t)(scr(clear_code) | (12u << 12));                \
-                        ws = cs + 1u;                                                           \
-                        wtag = ws << 12;                                                        \
-                        mask = (1u << ws) - inc;                                                \
-                        until = mask - first_code + 1u;                                         \
-                        ncs = scr(first_code);                                                  \
-                        if (TMEM) {                                                             \
-                            tmem_clear(tb);                                                     \
-                        } else {                                                                \
-                            __syncwarp();                                                       \
-                            clear_table(table, lane);                                           \
+                ncs += kScr;                                                                    \
+                if (MODE == 1) {                                                                \
+                    until--;                                                                    \
+                    if (!FIXED && until == 0u) { /* new index == mask, encoder.rs:326 */        \
+                        if (ws < 12u) {          /* encoder.rs:327-328 */                       \
+                            ws++;                                                               \
+                            wtag = ws << 12;                                                    \
+                            const uint32_t nm = (1u << ws) - inc;                               \
+                            until = nm - mask;                                                  \
+                            mask = nm;                                                          \
+                        } else { /* encoder.rs:329-333: clear at 12 bits, dictionary restarts */ \
+                            sts_u16(cpa, scr(clear_code) | (12u << 12));                        \
+                            cpa += 2u;                                                          \
+                            ws = cs + 1u;                                                       \
+                            wtag = ws << 12;                                                    \
+                            mask = (1u << ws) - inc;                                            \
+                            until = mask - first_code + 1u;                                     \
+                            ncs = scr(first_code);                                              \
+                            if (TMEM) {                                                         \
+                                tmem_clear(tb);                                                 \
+                            } else {                                                            \
+                                __syncwarp();                                                   \
+                                clear_table(table, lane);                                       \
+                            }                                                                   \
                         }                                                                       \
                     }                                                                           \
                 }                                                                               \
@@ -423,12 +442,13 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
     }
 #undef SLZW_STEP_B
 
+    if (MODE == 0) until -= (cpa - cpa0) >> 1;  // one insert per emitted code
     m.t = t;
-    m.ncs = ncs;
+    m.ncs = ncs & 0xFFFu;
     m.ws = ws;
     m.mask = mask;
     m.until = until;
-    m.ncodes = cp;
+    m.ncodes = (cpa - cbase) >> 1;
 }
 
 // The 32-bit word of lane `lane` of the tile whose first byte is at `p` (skew = p & 3): the
@@ -516,11 +536,13 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     };
 
     // Whole warp: bit-pack the buffered codes, flush complete words.
-    auto pack_and_flush = [&](uint32_t count) {
+    // An entry without a width tag (stored by a match loop that cannot meet a width change) takes
+    // the width `wdef`.
+    auto pack_and_flush = [&](uint32_t count, uint32_t wdef) {
         for (uint32_t base = 0; base < count; base += kWarpSize) {
             const uint32_t idx = base + lane;
             const uint32_t e = idx < count ? codes[idx] : 0u;
-            const uint32_t wd = e >> 12;
+            const uint32_t wd = idx < count ? ((e >> 12) ? (e >> 12) : wdef) : 0u;
             const uint32_t code = unscr(e) & ((1u << wd) - 1u);  // BitWriter masks to the width
             uint32_t x = wd;
 #pragma unroll
@@ -611,19 +633,29 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
         const uint32_t wn = nlen ? load_tile_word(src + npos, 0u, nlen, lane) : 0u;
         __syncwarp();
 
+        const uint32_t ws_tile = m.ws;  // width of the codes a MODE 0 / 2 tile stores without a tag
         if (len) {
-            if (TMEM)
-                match_tile_bucket<FIXED, true, U>(table, 0u, tb, rec, codes, lane, len, m, cs, inc,
-                                                  clear_code, first_code);
-            else if constexpr (BS)
-                match_tile_bucket<FIXED, false, U>(table, tb | (4u * (uint32_t)lane), 0u, rec, codes, lane,
-                                                   len, m, cs, inc, clear_code, first_code);
-            else
+            // inserts left before the next event against the most this tile can insert
+            const int mode = (FIXED && m.until == 0u) ? 2 : (m.until > len ? 0 : 1);
+#define SLZW_MATCH_B(TM, MD)                                                                        \
+    match_tile_bucket<FIXED, TM, U, MD>(table, TM ? 0u : (tb | (4u * (uint32_t)lane)), TM ? tb : 0u, rec, \
+                                        codes, lane, len, m, cs, inc, clear_code, first_code)
+            if (TMEM) {
+                if (mode == 0) SLZW_MATCH_B(true, 0);
+                else if (mode == 1) SLZW_MATCH_B(true, 1);
+                else if constexpr (FIXED) SLZW_MATCH_B(true, 2);
+            } else if constexpr (BS) {
+                if (mode == 0) SLZW_MATCH_B(false, 0);
+                else if (mode == 1) SLZW_MATCH_B(false, 1);
+                else if constexpr (FIXED) SLZW_MATCH_B(false, 2);
+            } else {
                 match_tile<FIXED, U>(table, tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
+            }
+#undef SLZW_MATCH_B
         }
         __syncwarp();
 
-        pack_and_flush(m.ncodes);
+        pack_and_flush(m.ncodes, ws_tile);
         m.ncodes = 0;
         // The `&mut [u8]` writer fails at the first byte past the slot (io.rs:244 / 307).  Codes
         // are emitted in input order, so a write failure inside this tile precedes a rejected
@@ -647,7 +679,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
         if (!FIXED) push(eoi, m.ws);                                            // encoder.rs:303 / 340
     }
     __syncwarp();
-    pack_and_flush(m.ncodes);
+    pack_and_flush(m.ncodes, m.ws);
     m.ncodes = 0;
     if (status == SLZW_OK && bits > limit) status = SLZW_ERR_IO_WRITE_ZERO;
     const bool finished = (status == SLZW_OK);  // the encoder reached fill()
