@@ -309,6 +309,14 @@ __global__ void __launch_bounds__(WARPS * kWarpSize, 1) slzw_decode_exact_kernel
 
 
 // ---- fast kernel ---------------------------------------------------------------------------------
+// Gather load of one already decoded byte.  A volatile asm statement: the compiler may not sink it
+// below the stores that follow (it cannot see that they never alias).
+__device__ __forceinline__ uint8_t ld_byte(const uint8_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.u8 %0, [%1];\n" : "=r"(v) : "l"(p));
+    return (uint8_t)v;
+}
+
 constexpr int kFastWin = 1024;   // output bytes one step may produce (32 mask words)
 constexpr int kFastTile = 512;   // compressed bytes staged per tile
 constexpr uint32_t kLit = 0x80000000u;
@@ -365,15 +373,17 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
 
     for (;;) {
         // ---- how many codes this step may read at the current width ----
-        const uint64_t avail64 = (total_bits - bitpos) / w;
-        if (avail64 == 0) {
+        // whole codes left in the input, capped at 32 (no 64-bit division in the common case)
+        const uint64_t rem_bits = total_bits - bitpos;
+        const uint32_t avail = rem_bits >= 32u * 12u ? 32u : (uint32_t)rem_bits / w;
+        if (avail == 0) {
             // fixed: the iterator ends, decoder.rs:585 (leftover bits ignored, io.rs:62-64);
             // variable: read_exact fails, Io(UnexpectedEof), decoder.rs:220 -- the bytes written
             // so far stay (this is how SURVEY.md F1 streams end)
             if (!fixed) status = SLZW_ERR_IO_UNEXPECTED_EOF;
             break;
         }
-        uint32_t bmax = avail64 < 32 ? (uint32_t)avail64 : 32u;
+        uint32_t bmax = avail < 32u ? avail : 32u;
         const uint32_t adj = hp ? 0u : 1u;   // the first code after a clear creates no entry
         if (!(fixed && nidx >= (uint32_t)kMaxTable)) {
             const uint32_t room = (w < 12u ? mask : (uint32_t)kMaxTable) - nidx + adj;
@@ -544,16 +554,19 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
                         }
                         cnt = x - cnt;
                     }
-                    for (uint32_t r = 0; r < nr; r++) {
+                    // Output byte 32 * r + lane of the step: which word it belongs to, where that
+                    // word's bytes come from.  Sources that lie inside this step are followed (they
+                    // strictly decrease) until they leave it.  Returns the byte, or the output
+                    // offset to load it from (kLit clear).
+                    auto resolve = [&](uint32_t r, bool& on) -> uint32_t {
                         const uint32_t m = __shfl_sync(kFullMask, wbits, (int)r);
                         const uint32_t cb = __shfl_sync(kFullMask, cnt, (int)r);
-                        const uint32_t ob = 32u * r + (uint32_t)lane;  // output byte of this lane
-                        const bool on = ob < total;
+                        const uint32_t ob = 32u * r + (uint32_t)lane;
+                        on = ob < total;
                         int own = (int)(cb + (uint32_t)__popc(m & lanemask_le)) - 1;
                         if (!on) own = 0;
                         uint32_t sp = __shfl_sync(kFullMask, srci, own);
                         uint32_t i = ob - __shfl_sync(kFullMask, pos, own);
-                        // sources that lie inside this step: follow them (they strictly decrease)
                         for (;;) {
                             const bool inb = on && !(sp & kLit) && sp + i >= produced;
                             if (!__any_sync(kFullMask, inb)) break;
@@ -568,7 +581,25 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
                                 i = rel - p2;
                             }
                         }
-                        if (on) dst[produced + ob] = (sp & kLit) ? (uint8_t)sp : dst[sp + i];
+                        return (sp & kLit) ? sp : sp + i;
+                    };
+                    // two rounds at a time: both gathers are in flight before the first store
+                    // (all sources lie below `produced`, the stores at or above it)
+                    uint32_t r = 0;
+                    for (; r + 2u <= nr; r += 2u) {
+                        bool on0, on1;
+                        const uint32_t s0 = resolve(r, on0);
+                        const uint32_t s1 = resolve(r + 1u, on1);
+                        uint8_t v0 = (uint8_t)s0, v1 = (uint8_t)s1;
+                        if (on0 && !(s0 & kLit)) v0 = ld_byte(dst + s0);
+                        if (on1 && !(s1 & kLit)) v1 = ld_byte(dst + s1);
+                        if (on0) dst[produced + 32u * r + (uint32_t)lane] = v0;
+                        if (on1) dst[produced + 32u * (r + 1u) + (uint32_t)lane] = v1;
+                    }
+                    if (r < nr) {
+                        bool on0;
+                        const uint32_t s0 = resolve(r, on0);
+                        if (on0) dst[produced + 32u * r + (uint32_t)lane] = (s0 & kLit) ? (uint8_t)s0 : ld_byte(dst + s0);
                     }
                     if ((uint32_t)lane < nr_set) S.bits[lane] = 0u;
                 }
