@@ -17,7 +17,8 @@
 // decoded output and stores it, coalesced.  Anything that is not the plain, successful case --
 // a code beyond the table, a missing clear code, input that ends before the end-of-information
 // code, a first code after a clear that is not a root (decoder.rs:230-236), a full output slot,
-// a word longer than the reference's stack, a slot larger than 1 MiB (offsets are 20 bits) --
+// a word longer than the reference's stack, more than 1 MiB of output between two clear codes
+// (entries hold 20-bit offsets relative to the last clear) --
 // makes the kernel DEFER the stream: it is appended to a retry list and decoded again, from
 // scratch, by the exact kernel.
 //
@@ -320,7 +321,9 @@ __device__ __forceinline__ uint8_t ld_byte(const uint8_t* p) {
 constexpr int kFastWin = 1024;   // output bytes one step may produce (32 mask words)
 constexpr int kFastTile = 512;   // compressed bytes staged per tile
 constexpr uint32_t kLit = 0x80000000u;
-constexpr uint32_t kFastMaxOut = 1u << 20;  // table entries hold 20-bit output offsets
+// Table entries hold 20-bit output offsets relative to the output position of the last clear
+// code (entries never outlive a clear): a dictionary generation may span 1 MiB of output.
+constexpr uint32_t kFastMaxSpan = 1u << 20;
 
 struct FastWarpSmem {
     uint32_t table[kMaxTable];           // entry = output offset << 12 | length
@@ -339,7 +342,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
         const uint64_t ob = a.out_off[sid];
         dst = a.out + ob;
         cap = a.out_off[sid + 1] - ob;
-        if (cap > kFastMaxOut) return false;
+        if (cap >= 0x80000000ull) return false;  // offsets are 31 bits + literal flag
     }
     const bool fixed = a.p.flavour == SLZW_FLAVOUR_FIXED;
     const bool big = a.p.big_endian != 0;
@@ -361,6 +364,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
     uint32_t mask = (1u << w) - inc;         // decoder.rs:211
     uint32_t nidx = first_index;             // next_index
     bool hp = false;                         // previous_code.is_some()
+    uint32_t seg_base = 0;                   // output position of the last clear code
     uint32_t prev_off = 0, prev_len = 0;     // the previous word, in the output
     uint64_t bitpos = 0;
     const uint64_t total_bits = n * 8;
@@ -459,7 +463,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
                 } else if (c < nidx) {
                     const uint32_t e = S.table[c];
                     len = e & 0xFFFu;
-                    srci = e >> 12;
+                    srci = seg_base + (e >> 12);
                 } else {  // c <= ni: an entry created inside this step, or the one being created
                     qd = (int)(c - nidx + adj) - 1;
                 }
@@ -514,6 +518,9 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
                 if (qd >= 0) srci = produced + pq;
                 else if (qd == -1) srci = prev_off;
             }
+            // offsets of this step's entries must fit the entry format
+            if (dst && !(fixed && nidx >= (uint32_t)kMaxTable) && produced + total - seg_base >= kFastMaxSpan)
+                return false;
             // ---- new entries (decoder.rs:272-276 / 630-634) ----
             {
                 uint32_t poff = produced + __shfl_up_sync(kFullMask, pos, 1);
@@ -524,7 +531,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
                 }
                 const uint32_t idx = nidx + (uint32_t)lane - adj;
                 if (act2 && (uint32_t)lane >= adj && idx < (uint32_t)kMaxTable)
-                    S.table[idx] = (poff << 12) | ((plen + 1u) & 0xFFFu);
+                    S.table[idx] = ((poff - seg_base) << 12) | ((plen + 1u) & 0xFFFu);
             }
             // ---- copy ----
             if (dst) {
@@ -629,6 +636,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
             mask = (1u << w) - inc;
             nidx = first_index;
             hp = false;
+            seg_base = produced;
         }
     }
 

@@ -428,12 +428,12 @@ def test_host_paths_with_many_small_chunks(monkeypatch):
 
 # ---- fast decoder: deferral to the exact kernel ---------------------------------------------------
 def test_fast_decoder_defers_what_it_cannot_reproduce(codec):
-    """Slots larger than 1 MiB (20-bit offsets), a first code that is not a root (stale-table
-    semantics, decoder.rs:230-236) and a missing clear code go to the exact kernel; the result
-    still equals the oracle's, and the diagnostics name the deferred streams."""
+    """More than 1 MiB of output between two clear codes (20-bit offsets), a first code that is
+    not a root (stale-table semantics, decoder.rs:230-236) and a missing clear code go to the exact
+    kernel; the result still equals the oracle's, and the diagnostics name the deferred streams."""
     rng = np.random.default_rng(5)
     p = O.tiff()
-    big = T.make_stream(rng, "runs", 1_300_000, 255).tobytes()           # output > 1 MiB
+    big = bytes(2_500_000)                                                # one dictionary generation
     st, _, big_packed = O.encode(p, big)
     assert st == 0
     small = T.make_stream(rng, "text", 5000, 255).tobytes()
@@ -451,6 +451,20 @@ def test_fast_decoder_defers_what_it_cannot_reproduce(codec):
     assert int(o_dst[2]) == O.ERR_UNEXPECTED_CODE and int(o_ddet[2]) == 258   # decoder.rs:759-769
     deferred = set(int(i) for i in codec.last_deferred())
     assert 0 in deferred and 1 not in deferred
+
+
+def test_fast_decoder_large_outputs_stay_on_the_fast_path(codec):
+    """Outputs larger than 1 MiB are fine as long as no dictionary generation spans 1 MiB."""
+    rng = np.random.default_rng(6)
+    for p, kind in ((O.tiff(), "runs"), (O.gif(6), "walk"), (O.gif(8), "text")):
+        raw = T.make_stream(rng, kind, 3_000_000, T.max_symbol(p)).tobytes()
+        st, _, packed = O.encode(p, raw)
+        assert st == 0
+        got = codec.decode(gp(p), packed, cap=len(raw))
+        want = O.decode(p, packed, cap=len(raw))
+        assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], T.pname(p)
+        assert got[2] == raw or want[0] != 0
+        assert len(codec.last_deferred()) == 0, T.pname(p)
 
 
 def test_fast_decoder_long_words_and_in_step_sources(codec):
