@@ -828,10 +828,13 @@ using Enc0 = EncConfig<96, 12, 16, 2, true>;    // default: 28 streams per SM, b
 using Enc1 = EncConfig<128, 12, 0, 4, false>;   // shared memory only, scalar speculative probes
 using Enc2 = EncConfig<96, 12, 16, 2, false>;   // scalar probes in shared memory, buckets in TMEM
 
-static int g_enc_config = 0;
+// -1 = choose per launch: a batch with no more streams than there are shared-memory
+// dictionaries on the device is bound by the latency of its longest stream, and the scalar
+// speculative probe has the shorter chain per input byte (config 4 at 512 frames of 1 MiB per
+// GPU); anything larger wants the 28 streams per SM and the fewest instructions per byte.
+static int g_enc_config = -1;
 
-void encode_select_config(int c) { g_enc_config = (c >= 0 && c <= 2) ? c : 0; }
-int encode_streams_per_sm() { return g_enc_config == 1 ? 12 : 28; }
+void encode_select_config(int c) { g_enc_config = (c >= 0 && c <= 2) ? c : -1; }
 
 cudaError_t encode_configure() {
     cudaError_t e = Enc0::configure();
@@ -841,7 +844,9 @@ cudaError_t encode_configure() {
 }
 
 cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
-    switch (g_enc_config) {
+    int cfg = g_enc_config;
+    if (cfg < 0) cfg = a.n <= (uint64_t)num_sms * 12u ? 1 : 0;
+    switch (cfg) {
         case 1: return Enc1::launch(a, num_sms, stream);
         case 2: return Enc2::launch(a, num_sms, stream);
         default: return Enc0::launch(a, num_sms, stream);

@@ -117,15 +117,26 @@ __device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8
     if (tail0 + lane < len) dst[tail0 + lane] = src[tail0 + lane];
 }
 
+// One block per stream at a time; the warps of the block take 4 KB pieces of it, so a batch of a
+// few long streams (1 MiB GIF frames) spreads over the whole device as well as one of many strips.
+constexpr uint64_t kGatherPiece = 4096;
+
 __global__ void compact_gather_kernel(const uint8_t* __restrict__ src,
                                       const uint64_t* __restrict__ src_off,
                                       const uint64_t* __restrict__ len, uint64_t n,
                                       uint8_t* __restrict__ dst, const uint64_t* __restrict__ dst_off) {
     const int lane = threadIdx.x % kWarpSize;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) / kWarpSize;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) / kWarpSize;
-    for (uint64_t i = warp; i < n; i += nwarps)
-        warp_copy(dst + dst_off[i], src + src_off[i], len[i], lane);
+    const uint64_t warp = threadIdx.x / kWarpSize;
+    const uint64_t warps = blockDim.x / kWarpSize;
+    for (uint64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint64_t l = len[i];
+        const uint8_t* s = src + src_off[i];
+        uint8_t* d = dst + dst_off[i];
+        for (uint64_t o = warp * kGatherPiece; o < l; o += warps * kGatherPiece) {
+            const uint64_t m = l - o < kGatherPiece ? l - o : kGatherPiece;
+            warp_copy(d + o, s + o, m, lane);
+        }
+    }
 }
 
 }  // namespace
@@ -151,10 +162,9 @@ cudaError_t compact_launch(const uint8_t* src, const uint64_t* src_off, const ui
                            cudaStream_t stream) {
     compact_scan_kernel<<<1, 1024, 0, stream>>>(len, n, align ? align : 1, dst_off);
     const int threads = 256;
-    const uint64_t want = (n * kWarpSize + threads - 1) / threads;
-    const uint64_t cap = (uint64_t)num_sms * 16;
-    compact_gather_kernel<<<(int)(want < cap ? want : cap), threads, 0, stream>>>(src, src_off, len,
-                                                                                    n, dst, dst_off);
+    const uint64_t cap = (uint64_t)num_sms * 8;
+    compact_gather_kernel<<<(int)(n < cap ? n : cap), threads, 0, stream>>>(src, src_off, len, n, dst,
+                                                                            dst_off);
     return cudaGetLastError();
 }
 

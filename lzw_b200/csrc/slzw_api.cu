@@ -17,7 +17,6 @@
 namespace slzw {
 // encode_kernels.cu
 void encode_select_config(int c);
-int encode_streams_per_sm();
 cudaError_t encode_configure();
 cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream);
 // decode_kernels.cu
