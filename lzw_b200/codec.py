@@ -196,6 +196,31 @@ class Codec:
         return status_message(is_decoder, status, detail, code_size)
 
 
+class PinnedBuffer:
+    """Page-locked host memory from slzw_host_alloc as a uint8 numpy array (`.array`).  The host
+    entry points copy to and from pinned memory asynchronously, and the encoder reads pinned input
+    in place."""
+
+    def __init__(self, nbytes: int):
+        self._lib = _lib.lib()
+        self._p = self._lib.slzw_host_alloc(max(int(nbytes), 1))
+        if not self._p:
+            raise MemoryError(f"slzw_host_alloc({nbytes}) failed")
+        self.array = np.ctypeslib.as_array(C.cast(self._p, C.POINTER(C.c_uint8)), shape=(max(int(nbytes), 1),))[:nbytes]
+
+    def free(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            self._lib.slzw_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def status_message(is_decoder: bool, status: int, detail: int, code_size: int = 0) -> str:
     """The reference's Display text for a result (encoder.rs:31-44, decoder.rs:27-42)."""
     buf = C.create_string_buffer(160)

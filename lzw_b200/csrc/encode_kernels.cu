@@ -452,14 +452,21 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
 }
 
 // The 32-bit word of lane `lane` of the tile whose first byte is at `p` (skew = p & 3): the
-// aligned word at p - skew + 4 * lane, or 0 when it holds no byte of [p, p + tile_len).  An
-// aligned word that holds at least one byte of the stream is read whole.
+// aligned word at p - skew + 4 * lane, or 0 when it holds no byte of [p, p + tile_len).  A word
+// that lies partly outside the tile is assembled from byte loads, so nothing outside
+// [p, p + tile_len) is ever touched (the input may be pinned host memory read in place).
 __device__ __forceinline__ uint32_t load_tile_word(const uint8_t* __restrict__ p, uint32_t skew,
                                                    uint32_t tile_len, int lane) {
     const uint32_t lo = 4u * (uint32_t)lane;
-    if (lo + 3u >= skew && lo < skew + tile_len)
-        return __ldg(reinterpret_cast<const uint32_t*>(p - skew + lo));
-    return 0u;
+    const uint32_t end = skew + tile_len;
+    if (lo >= skew && lo + 4u <= end) return __ldg(reinterpret_cast<const uint32_t*>(p - skew + lo));
+    uint32_t v = 0u;
+    if (lo + 3u >= skew && lo < end) {
+#pragma unroll
+        for (uint32_t b = 0; b < 4u; b++)
+            if (lo + b >= skew && lo + b < end) v |= (uint32_t)__ldg(p - skew + lo + b) << (8u * b);
+    }
+    return v;
 }
 
 // tmem (warp-uniform) = the stream's dictionary lives in tensor memory at address `tb` (table is

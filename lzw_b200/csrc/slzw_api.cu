@@ -131,6 +131,7 @@ struct slzw_ctx {
     // chunk of streams, the kernels of the previous chunk and the D2H copy of the one before
     // overlap (PCIe is full duplex)
     HostSlot pipe[kPipe];
+    bool zero_copy_in = true;  // SLZW_HOST_ZERO_COPY=0 stages pinned input like pageable input
     uint64_t enc_chunk_bytes = kEncChunkBytes;
     uint64_t dec_chunk_bytes = kDecChunkBytes;
     uint64_t launches = 0;
@@ -271,6 +272,19 @@ int run_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, cu
     return finish(ctx, w, stream);
 }
 
+// Pinned (page-locked, mapped) host memory can be read by the kernels in place: returns the device
+// alias of `p`, or nullptr for pageable memory.  The encoder reads every input byte exactly once,
+// one tile ahead of its use, so its input never needs a staging copy.
+const uint8_t* device_alias(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();  // not an error: plain malloc memory on older drivers
+        return nullptr;
+    }
+    if (attr.type == cudaMemoryTypeHost && attr.devicePointer) return (const uint8_t*)attr.devicePointer;
+    return nullptr;
+}
+
 // Splits streams [0, n) into chunks of roughly equal weight (weight[i+1] - weight[i] per stream).
 std::vector<uint64_t> chunk_bounds(const uint64_t* weight, uint64_t n, uint64_t chunk_bytes) {
     const uint64_t total = weight[n] - weight[0];
@@ -335,6 +349,9 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
         chunk_bounds(needs_out && op == Op::Decode ? b->out_off : b->in_off, n,
                      op == Op::Encode ? ctx->enc_chunk_bytes : ctx->dec_chunk_bytes);
     const size_t chunks = cb.size() - 1;
+    // encode: pinned input is read in place (the decoder's input is small and its access pattern
+    // re-reads tiles, it stays staged)
+    const uint8_t* in_alias = (op == Op::Encode && ctx->zero_copy_in) ? device_alias(b->in) : nullptr;
 
     auto enqueue = [&](size_t k) -> int {
         HostSlot& hs = ctx->pipe[k % kPipe];
@@ -344,7 +361,7 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
         const uint64_t out_lo = needs_out ? b->out_off[s0] : 0, out_hi = needs_out ? b->out_off[s1] : 0;
         {
             std::lock_guard<std::mutex> lock(ctx->mu);
-            CK(hs.in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
+            if (!in_alias) CK(hs.in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
             CK(hs.out.reserve(out_hi - out_lo + 16), "cudaMalloc(out)");
             CK(hs.in_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(in_off)");
             CK(hs.out_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(out_off)");
@@ -360,7 +377,7 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
         if (needs_out) memcpy(st.out_off, b->out_off + s0, sizeof(uint64_t) * (m + 1));
         if (b->code_size) memcpy(st.cs, b->code_size + s0, m);
         // Offsets stay absolute: the device copies of in/out are biased by -lo instead.
-        if (in_hi > in_lo)
+        if (!in_alias && in_hi > in_lo)
             CK(cudaMemcpyAsync(hs.in.p, b->in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
         CK(cudaMemcpyAsync(hs.in_off.p, st.in_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
            "H2D in_off");
@@ -369,7 +386,7 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
                "H2D out_off");
         if (b->code_size) CK(cudaMemcpyAsync(hs.cs.p, st.cs, m, cudaMemcpyHostToDevice, s), "H2D code_size");
         slzw_batch d = {};
-        d.in = (const uint8_t*)hs.in.p - in_lo;
+        d.in = in_alias ? in_alias : (const uint8_t*)hs.in.p - in_lo;
         d.in_off = (const uint64_t*)hs.in_off.p;
         d.out = needs_out ? (uint8_t*)hs.out.p - out_lo : nullptr;
         d.out_off = needs_out ? (const uint64_t*)hs.out_off.p : nullptr;
@@ -431,6 +448,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
     const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->enc_chunk_bytes);
     const size_t chunks = cb.size() - 1;
+    const uint8_t* in_alias = ctx->zero_copy_in ? device_alias(in) : nullptr;  // pinned input: read in place
     uint64_t hbase = 0;  // dense bytes placed so far
     bool overflow = false;
 
@@ -456,7 +474,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         if (code_size) memcpy(st.cs, code_size + s0, m);
         {
             std::lock_guard<std::mutex> lock(ctx->mu);
-            CK(hs.in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
+            if (!in_alias) CK(hs.in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
             CK(hs.out.reserve(slot_bytes + 16), "cudaMalloc(slots)");
             CK(hs.dense.reserve(slot_bytes + align * m + 16), "cudaMalloc(dense)");
             CK(hs.in_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(in_off)");
@@ -467,7 +485,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
             CK(hs.detail.reserve(sizeof(uint32_t) * m), "cudaMalloc(detail)");
             if (code_size) CK(hs.cs.reserve(m), "cudaMalloc(code_size)");
         }
-        if (in_hi > in_lo)
+        if (!in_alias && in_hi > in_lo)
             CK(cudaMemcpyAsync(hs.in.p, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
         CK(cudaMemcpyAsync(hs.in_off.p, st.in_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
            "H2D in_off");
@@ -475,7 +493,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
            "H2D slots");
         if (code_size) CK(cudaMemcpyAsync(hs.cs.p, st.cs, m, cudaMemcpyHostToDevice, s), "H2D code_size");
         slzw_batch d = {};
-        d.in = (const uint8_t*)hs.in.p - in_lo;
+        d.in = in_alias ? in_alias : (const uint8_t*)hs.in.p - in_lo;
         d.in_off = (const uint64_t*)hs.in_off.p;
         d.out = (uint8_t*)hs.out.p;
         d.out_off = (const uint64_t*)hs.out_off.p;
@@ -578,6 +596,7 @@ int slzw_create(int device, slzw_ctx** out) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SLZW_ENC_CONFIG")) encode_select_config(atoi(e));  // tuning knob
+    if (const char* e = getenv("SLZW_HOST_ZERO_COPY")) ctx->zero_copy_in = atoi(e) != 0;
     if (const char* e = getenv("SLZW_HOST_CHUNK_BYTES")) {
         const long long v = atoll(e);  // tests use tiny chunks
         if (v > 0) ctx->enc_chunk_bytes = ctx->dec_chunk_bytes = (uint64_t)v;

@@ -426,6 +426,34 @@ def test_host_paths_with_many_small_chunks(monkeypatch):
         c.close()
 
 
+def test_host_paths_with_pinned_buffers_read_in_place(monkeypatch):
+    """Pinned input is read by the encoder in place (no staging copy), also at odd offsets inside the
+    pinned allocation and with a last stream that ends on the allocation's last byte."""
+    import lzw_b200
+    monkeypatch.setenv("SLZW_HOST_CHUNK_BYTES", "50000")
+    c = lzw_b200.Codec(0)
+    try:
+        p = O.tiff()
+        buf, off = T.make_batch(123, 150, 255, max_len=7000)
+        for shift in (0, 1, 3):
+            pin = lzw_b200.PinnedBuffer(buf.size + shift)
+            view = pin.array[shift:]
+            view[:] = buf
+            slots = np.zeros(off.size, dtype=np.uint64)
+            slots[1:] = np.cumsum([O.encode_bound(int(l)) for l in np.diff(off)])
+            o_out, o_len, o_st, o_det = O.encode_batch(p, buf, off, slots)
+            dense, doff, st, det = c.encode_batch_dense(gp(p), view, off)
+            assert np.array_equal(st, o_st) and np.array_equal(np.diff(doff), o_len)
+            for i in range(o_len.size):
+                assert np.array_equal(dense[int(doff[i]):int(doff[i + 1])],
+                                      o_out[int(slots[i]):int(slots[i]) + int(o_len[i])]), (shift, i)
+            out, _, out_len, st2, _ = c.encode_batch(gp(p), view, off, out_off=slots)
+            assert np.array_equal(out_len, o_len) and T.slots_equal(out, o_out, slots, o_len) == -1
+            pin.free()
+    finally:
+        c.close()
+
+
 # ---- fast decoder: deferral to the exact kernel ---------------------------------------------------
 def test_fast_decoder_defers_what_it_cannot_reproduce(codec):
     """More than 1 MiB of output between two clear codes (20-bit offsets), a first code that is

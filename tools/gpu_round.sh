@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee -a gpurun_out/pytest.log
-timeout 600 python tools/profile_step.py --config 4 --streams 512 --passes 2 --what encode 2>&1 | grep -v Warning | tail -1 | tee -a gpurun_out/step.log
-timeout 300 python tools/profile_step.py --streams 65536 --passes 2 2>&1 | grep -v Warning | tail -3 | tee -a gpurun_out/step.log
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee -a gpurun_out/pytest.log
+python tools/e2e_probe.py 2>&1 | grep -v Warning | tee gpurun_out/e2e_probe2.log
