@@ -376,7 +376,10 @@ def run_ours(args):
         dt = float(te.item())
         e2e = {"value": world * total * e2e_steps / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
-               "steps": e2e_steps, "round_trip_ok": bool(np.array_equal(dec[:total], buf))}
+               "steps": e2e_steps, "round_trip_ok": bool(np.array_equal(dec[:total], buf)),
+               "note": "slzw_encode_batch_host_dense + slzw_decode_batch_host on pinned host buffers; the "
+                       "encoder reads its pinned input in place over PCIe (counted in h2d_bytes_per_step), "
+                       "everything else is cudaMemcpyAsync inside the call"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
