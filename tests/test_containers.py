@@ -1,0 +1,121 @@
+"""Container framing: GIF image data sub-blocks and TIFF strip tables around the
+codec's raw LZW streams, checked with an independent decoder (PIL: its own GIF LZW decoder, libtiff
+for TIFF).  CPU tests use the oracle's streams (the checker), GPU tests the codec's."""
+import io
+import os
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from lzw_b200 import containers as K
+from oracle import oracle as O
+from tests import cases as T
+from tests.conftest import GOLDEN
+
+
+def _tokyo():
+    im = Image.open(os.path.join(GOLDEN, "tokyo_128_colors.png"))   # 1024 x 684, 128 colours
+    pal = im.getpalette()
+    palette = [tuple(pal[3 * i:3 * i + 3]) for i in range(128)]
+    return np.asarray(im).copy(), palette
+
+
+def _sunflower():
+    with open(os.path.join(GOLDEN, "sunflower.bmp"), "rb") as f:
+        raw = np.frombuffer(f.read()[54:], dtype=np.uint8)
+    rows = raw.reshape(200, 544)[:, :543].reshape(200, 181, 3)        # drop the BMP row padding
+    return np.ascontiguousarray(rows[::-1, :, ::-1])                    # bottom-up BGR -> top-down RGB
+
+
+def test_gif_sub_blocks_round_trip():
+    rng = np.random.default_rng(1)
+    for n in (0, 1, 254, 255, 256, 510, 511, 70000):
+        stream = rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+        framed = K.gif_image_data(7, stream)
+        assert framed[0] == 7 and framed[-1] == 0 and len(framed) == 2 + n + (n + 254) // 255
+        mcs, back, pos = K.parse_gif_image_data(framed)
+        assert (mcs, back, pos) == (7, stream, len(framed))
+
+
+def test_oracle_gif_stream_is_a_real_gif():
+    """The reference's GIF-style stream (here: the oracle's) framed as GIF image data decodes with
+    PIL's own LZW decoder to the original pixels (compare_crates.rs encodes exactly this image)."""
+    px, palette = _tokyo()
+    st, _, stream = O.encode(O.gif(7), px.tobytes())
+    assert st == 0
+    data = K.write_gif(px.shape[1], px.shape[0], palette, [stream], 7)
+    im = Image.open(io.BytesIO(data))
+    assert im.size == (px.shape[1], px.shape[0])
+    assert np.array_equal(np.asarray(im.convert("P") if im.mode != "P" else im), px)
+    frames = K.read_gif_frames(data)
+    assert frames == [(px.shape[1], px.shape[0], 7, stream)]
+
+
+def test_oracle_tiff_strips_are_a_real_tiff():
+    """TIFF-style strips inside a baseline TIFF decode with libtiff (through PIL)."""
+    px = _sunflower()
+    buf, off = K.strips_of_image(px, rows_per_strip=16)
+    strips = []
+    for i in range(off.size - 1):
+        st, _, s = O.encode(O.tiff(), buf[int(off[i]):int(off[i + 1])].tobytes())
+        assert st == 0
+        strips.append(s)
+    data = K.write_tiff_lzw(px.shape[1], px.shape[0], 3, 16, strips)
+    im = Image.open(io.BytesIO(data))
+    assert np.array_equal(np.asarray(im), px)
+    w, h, spp, rps, back = K.read_tiff_strips(data)
+    assert (w, h, spp, rps) == (181, 200, 3, 16) and back == strips
+
+
+@pytest.mark.gpu
+def test_gpu_gif_frames_decode_with_pil():
+    """Frames encoded by the GPU codec in one batch, framed, read back by PIL; then the streams
+    are pulled out of the file again and decoded by the batched GPU decoder."""
+    import lzw_b200
+    from lzw_b200.types import gif_params
+    codec = lzw_b200.Codec(0)
+    try:
+        px, palette = _tokyo()
+        frames = np.stack([px, px[::-1], np.roll(px, 77, axis=1)])
+        off = np.arange(4, dtype=np.uint64) * np.uint64(px.size)
+        dense, doff, st, _ = codec.encode_batch_dense(gif_params(7), frames.reshape(-1), off)
+        assert (st == 0).all()
+        data = K.write_gif(px.shape[1], px.shape[0], palette, K.split_dense(dense, doff), 7)
+        im = Image.open(io.BytesIO(data))
+        for i in range(3):
+            im.seek(i)
+            assert np.array_equal(np.asarray(im.convert("RGB")),
+                                  np.asarray(palette, dtype=np.uint8)[frames[i]]), i
+        got = K.read_gif_frames(data)
+        streams = [g[3] for g in got]
+        in_off = np.zeros(4, dtype=np.uint64)
+        in_off[1:] = np.cumsum([len(s) for s in streams])
+        dec, dlen, dst, _ = codec.decode_batch(gif_params(7), np.frombuffer(b"".join(streams), dtype=np.uint8),
+                                               in_off, off)
+        assert (dst == 0).all() and np.array_equal(dec[: frames.size], frames.reshape(-1))
+    finally:
+        codec.close()
+
+
+@pytest.mark.gpu
+def test_gpu_tiff_strips_decode_with_libtiff():
+    import lzw_b200
+    from lzw_b200.types import tiff_params
+    codec = lzw_b200.Codec(0)
+    try:
+        px = _sunflower()
+        for rps in (1, 16, 200):
+            buf, off = K.strips_of_image(px, rows_per_strip=rps)
+            dense, doff, st, _ = codec.encode_batch_dense(tiff_params(), buf, off)
+            assert (st == 0).all()
+            data = K.write_tiff_lzw(px.shape[1], px.shape[0], 3, rps, K.split_dense(dense, doff))
+            assert np.array_equal(np.asarray(Image.open(io.BytesIO(data))), px), rps
+            w, h, spp, rps2, strips = K.read_tiff_strips(data)
+            in_off = np.zeros(len(strips) + 1, dtype=np.uint64)
+            in_off[1:] = np.cumsum([len(s) for s in strips])
+            dec, dlen, dst, _ = codec.decode_batch(tiff_params(), np.frombuffer(b"".join(strips), dtype=np.uint8),
+                                                   in_off, off)
+            assert np.array_equal(dec[: buf.size], buf)
+    finally:
+        codec.close()
