@@ -3,7 +3,8 @@
 // Two kernels, both one warp per stream, persistent CTAs, streams handed out through the
 // scheduler's work queue:
 //
-// slzw_decode_fast_kernel -- the throughput path.  The reference's prefix-chain walk
+// slzw_decode_fast_kernel -- the throughput path (32 warps per SM: 12 with their table in shared
+// memory, 20 with it in an L2-resident block of global memory).  The reference's prefix-chain walk
 // (decoder.rs:251-267) is replaced by an (output offset, length) table: entry n is the word that
 // was written for the previous code plus the first byte of the current word, and those bytes are
 // contiguous in the stream's own output, so an entry is just (offset of the previous word,
@@ -325,14 +326,20 @@ constexpr uint32_t kLit = 0x80000000u;
 // code (entries never outlive a clear): a dictionary generation may span 1 MiB of output.
 constexpr uint32_t kFastMaxSpan = 1u << 20;
 
+// Per-warp working set besides the table.  The table itself (4096 entries = offset << 12 | length)
+// lives in shared memory for the first SW warps of a CTA and in global memory (a per-warp 16 KB
+// block of the context's scratch, L2-resident: 148 SMs x GW x 16 KB) for the other GW warps: the
+// kernel is latency-bound with the 13 warps per SM that shared memory has room for, and a table
+// lookup happens once per 32 codes, so paying L2 latency for it is cheap next to doubling the
+// number of streams in flight.
 struct FastWarpSmem {
-    uint32_t table[kMaxTable];           // entry = output offset << 12 | length
     uint32_t bits[kFastWin / 32];        // word starts of the current step
     __align__(16) uint8_t tile[kFastTile + 32];
 };
 
 // Returns false when the stream has to be decoded by the exact kernel.
-__device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem& S, int lane) {
+__device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, uint32_t* __restrict__ table,
+                                   FastWarpSmem& S, int lane) {
     const uint64_t in_begin = a.in_off[sid];
     const uint64_t n = a.in_off[sid + 1] - in_begin;
     const uint8_t* src = a.in + in_begin;
@@ -461,7 +468,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
                 } else if (!hp && lane == 0) {
                     bad = true;  // first code is not a root: stale-table semantics, decoder.rs:230-236
                 } else if (c < nidx) {
-                    const uint32_t e = S.table[c];
+                    const uint32_t e = table[c];
                     len = e & 0xFFFu;
                     srci = seg_base + (e >> 12);
                 } else {  // c <= ni: an entry created inside this step, or the one being created
@@ -531,7 +538,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
                 }
                 const uint32_t idx = nidx + (uint32_t)lane - adj;
                 if (act2 && (uint32_t)lane >= adj && idx < (uint32_t)kMaxTable)
-                    S.table[idx] = ((poff - seg_base) << 12) | ((plen + 1u) & 0xFFFu);
+                    table[idx] = ((poff - seg_base) << 12) | ((plen + 1u) & 0xFFFu);
             }
             // ---- copy ----
             if (dst) {
@@ -649,12 +656,15 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, FastWarpSmem
     return true;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * kWarpSize, 1) slzw_decode_fast_kernel(const DevBatch a) {
+template <int SW, int GW, int CTAS>
+__global__ void __launch_bounds__((SW + GW) * kWarpSize, CTAS) slzw_decode_fast_kernel(const DevBatch a) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x / kWarpSize;
     const int lane = threadIdx.x % kWarpSize;
-    FastWarpSmem& S = reinterpret_cast<FastWarpSmem*>(smem_raw)[warp];
+    // [SW tables][SW + GW working sets]
+    FastWarpSmem& S = reinterpret_cast<FastWarpSmem*>(smem_raw + (size_t)SW * kMaxTable * 4)[warp];
+    uint32_t* table = warp < SW ? reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * kMaxTable
+                                : a.dec_tables + ((size_t)blockIdx.x * GW + (size_t)(warp - SW)) * kMaxTable;
     for (int i = lane; i < kFastWin / 32; i += kWarpSize) S.bits[i] = 0u;
     __syncwarp();
     for (;;) {
@@ -663,7 +673,7 @@ __global__ void __launch_bounds__(WARPS * kWarpSize, 1) slzw_decode_fast_kernel(
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= a.n) break;
         const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-        const bool done = decode_stream_fast(a, sid, S, lane);
+        const bool done = decode_stream_fast(a, sid, table, S, lane);
         __syncwarp();
         if (!done) {
             // a deferred stream may have left word-start bits behind
@@ -696,21 +706,49 @@ cudaError_t decode_exact_launch(const DevBatch& a, int grid, cudaStream_t stream
 }
 
 
-constexpr int kFastWarps = 13;
+// {warps with the table in shared memory, warps with the table in global memory}
+template <int SW, int GW, int CTAS = 1>
+struct FastConfig {
+    static size_t smem() { return (size_t)SW * kMaxTable * 4 + sizeof(FastWarpSmem) * (SW + GW); }
+    static cudaError_t configure() {
+        return cudaFuncSetAttribute(slzw_decode_fast_kernel<SW, GW, CTAS>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
+    }
+    static cudaError_t launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
+        const uint64_t ctas = (a.n + SW + GW - 1) / (SW + GW);
+        const uint64_t cap = (uint64_t)num_sms * CTAS;
+        const int grid = (int)(ctas < cap ? ctas : cap);
+        slzw_decode_fast_kernel<SW, GW, CTAS><<<grid, (SW + GW) * kWarpSize, smem(), stream>>>(a);
+        return cudaGetLastError();
+    }
+};
 
-size_t decode_fast_smem_bytes() { return sizeof(FastWarpSmem) * kFastWarps; }
-int decode_fast_warps_per_cta() { return kFastWarps; }
+// 32 warps per SM saturate the kernel (26: 24.4 ms, 32: 22.2 ms, 40: 23.0 ms, 48: 24.0 ms for
+// config 3 at 65,536 strips; 13 with shared-memory tables only: 38.9 ms)
+using Fast0 = FastConfig<12, 20>;  // default
+using Fast1 = FastConfig<13, 0>;   // shared-memory tables only
+using Fast2 = FastConfig<0, 32>;   // global-memory tables only
+
+static int g_fast_config = 0;
+
+void decode_select_config(int c) { g_fast_config = (c >= 0 && c <= 2) ? c : 0; }
+
+// global-memory tables one decode launch needs (bytes)
+size_t decode_fast_table_bytes(int num_sms) { return (size_t)num_sms * 32 * kMaxTable * 4; }
 
 cudaError_t decode_fast_configure() {
-    return cudaFuncSetAttribute(slzw_decode_fast_kernel<kFastWarps>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)decode_fast_smem_bytes());
+    cudaError_t e = Fast0::configure();
+    if (e != cudaSuccess) return e;
+    if ((e = Fast1::configure()) != cudaSuccess) return e;
+    return Fast2::configure();
 }
 
-cudaError_t decode_fast_launch(const DevBatch& a, int grid, cudaStream_t stream) {
-    slzw_decode_fast_kernel<kFastWarps>
-        <<<grid, kFastWarps * kWarpSize, decode_fast_smem_bytes(), stream>>>(a);
-    return cudaGetLastError();
+cudaError_t decode_fast_launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
+    switch (g_fast_config) {
+        case 1: return Fast1::launch(a, num_sms, stream);
+        case 2: return Fast2::launch(a, num_sms, stream);
+        default: return Fast0::launch(a, num_sms, stream);
+    }
 }
 
 }  // namespace slzw

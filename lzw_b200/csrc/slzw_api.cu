@@ -24,10 +24,10 @@ size_t decode_exact_smem_bytes();
 int decode_exact_warps_per_cta();
 cudaError_t decode_exact_configure();
 cudaError_t decode_exact_launch(const DevBatch& a, int grid, cudaStream_t stream);
-size_t decode_fast_smem_bytes();
-int decode_fast_warps_per_cta();
+void decode_select_config(int c);
+size_t decode_fast_table_bytes(int num_sms);
 cudaError_t decode_fast_configure();
-cudaError_t decode_fast_launch(const DevBatch& a, int grid, cudaStream_t stream);
+cudaError_t decode_fast_launch(const DevBatch& a, int num_sms, cudaStream_t stream);
 // sched_kernels.cu
 int sched_size_classes();
 cudaError_t sched_build_order(const uint64_t* off, uint64_t n, uint32_t* hist, uint32_t* order,
@@ -72,6 +72,7 @@ struct Workspace {
     DevBuf hist;   // size classes
     DevBuf order;  // n u32
     DevBuf retry;  // n u32: streams the fast decoder deferred
+    DevBuf tables; // fast decoder: dictionaries of the warps that have none in shared memory
     cudaEvent_t done = nullptr;
     bool used = false;
 };
@@ -214,6 +215,7 @@ DevBatch make_dev_batch(const slzw_params* params, const slzw_batch* b, const Wo
     a.retry = (uint32_t*)((unsigned long long*)w->queue.p + 2);
     a.retry_ids = (uint32_t*)w->retry.p;
     a.n_dev = nullptr;
+    a.dec_tables = (uint32_t*)w->tables.p;
     a.p = *params;
     return a;
 }
@@ -258,8 +260,9 @@ int run_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, cu
         ctx->last_decode_ws = (int)(w - ctx->ws);
         const bool exact_only = getenv("SLZW_DECODE_EXACT") != nullptr;  // debugging knob
         if (!exact_only) {
-            CK(decode_fast_launch(a, grid_for(ctx, b->n, decode_fast_warps_per_cta()), stream),
-               "fast decode launch");
+            CK(w->tables.reserve(decode_fast_table_bytes(ctx->num_sms)), "cudaMalloc(decode tables)");
+            a.dec_tables = (uint32_t*)w->tables.p;
+            CK(decode_fast_launch(a, ctx->num_sms, stream), "fast decode launch");
             ctx->launches += 1;
             a.order = a.retry_ids;
             a.n_dev = a.retry;
@@ -596,6 +599,7 @@ int slzw_create(int device, slzw_ctx** out) {
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* e = getenv("SLZW_ENC_CONFIG")) encode_select_config(atoi(e));  // tuning knob
+    if (const char* e = getenv("SLZW_DEC_CONFIG")) decode_select_config(atoi(e));  // tuning knob
     if (const char* e = getenv("SLZW_HOST_ZERO_COPY")) ctx->zero_copy_in = atoi(e) != 0;
     if (const char* e = getenv("SLZW_HOST_CHUNK_BYTES")) {
         const long long v = atoll(e);  // tests use tiny chunks
@@ -628,6 +632,7 @@ void slzw_destroy(slzw_ctx* ctx) {
             w.hist.release();
             w.order.release();
             w.retry.release();
+            w.tables.release();
             if (w.done) cudaEventDestroy(w.done);
         }
         for (int i = 0; i < kPipe; i++) ctx->pipe[i].release();

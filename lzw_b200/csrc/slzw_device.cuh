@@ -26,6 +26,7 @@ struct DevBatch {
     uint32_t* retry;                // fast decode: number of streams deferred to the exact kernel
     uint32_t* retry_ids;            // fast decode: their ids
     const uint32_t* n_dev;          // exact decode of deferred streams: stream count on the device
+    uint32_t* dec_tables;           // fast decode: 16 KB table blocks of the warps without a shared-memory table
     slzw_params p;
 };
 
