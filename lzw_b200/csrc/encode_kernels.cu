@@ -341,7 +341,10 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
     const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(codes);
     uint32_t cpa = cbase + 2u * m.ncodes;         // shared address of the next code
     const uint32_t cpa0 = cpa;
-    const uint32_t lanebit = 1u << lane;
+    // a bucket fills from slot 0 upwards and nothing is ever removed, so its empty slots are
+    // always the lanes >= some count: the first empty slot is this lane's iff the ballot of empty
+    // slots equals "all lanes from mine on"
+    const uint32_t lanes_ge = 0xFFFFFFFFu << lane;
 
 #define SLZW_STEP_B(RC)                                                                         \
     {                                                                                           \
@@ -373,7 +376,7 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
             sts_u16(cpa, MODE == 1 ? ((t >> 20) | wtag) : (t >> 20));                           \
             cpa += 2u;                                                                          \
             if (MODE == 0 || (MODE == 1 && (!FIXED || until != 0u))) {                          \
-                const bool mine = (em & (0u - em)) == lanebit; /* first empty slot */           \
+                const bool mine = em == lanes_ge; /* I own the first empty slot */              \
                 const uint32_t entry = key | (ncs & 0xFFFu);                                    \
                 if (TMEM) {                                                                     \
                     tmem_st(a, mine ? entry : v);                                               \
