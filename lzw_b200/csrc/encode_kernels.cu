@@ -350,6 +350,10 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
     {                                                                                           \
         const uint32_t key = t | (RC).x;                                                        \
         uint32_t a = TMEM ? ((tp & 0x7Fu) ^ (RC).y) : (tl | ((tp ^ (RC).y) & kBucketMask));     \
+        /* One explicit convergence point per step: the compiler then drops the divergence guard \
+           it otherwise puts in front of every ballot and shuffle of the step (tcgen05.ld brings \
+           its own); it also orders the previous step's insert before this step's loads. */      \
+        if (!TMEM) __syncwarp();                                                                \
         _Pragma("unroll 1") for (;;) {                                                          \
             uint32_t v;                                                                         \
             if (TMEM) {                                                                         \
@@ -411,7 +415,6 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                         }                                                                       \
                     }                                                                           \
                 }                                                                               \
-                if (!TMEM) __syncwarp(); /* the new entry is visible to every lane's next load */ \
             }                                                                                   \
             t = (RC).x * (kScr << 8); /* prefix = this byte: (k * kScr mod 4096) << 20 */       \
             tp = TMEM ? t >> 20 : t >> 13;                                                      \
