@@ -1,0 +1,361 @@
+// salzweg.hpp -- C++17 mirror of the public interface of redwarp/lzw (crate `salzweg`) over the C
+// ABI of slzw.h.  Header-only; link with libslzw.so.
+//
+// The reference is a Rust crate and this repository's image has no Rust toolchain, so the host
+// side above the C ABI is C++: the same eight types with the same associated functions, argument
+// meaning and error behaviour as
+//   lzw/src/lib.rs:59-91                       Endianness, CodeSizeStrategy
+//   lzw/src/encoder.rs:16-52                   EncodingError (+ Display text)
+//   lzw/src/decoder.rs:16-50                   DecodingError (+ Display text)
+//   lzw/src/encoder.rs:199-220, 262-271        VariableEncoder::{encode, encode_to_vec}
+//   lzw/src/encoder.rs:392-399, 435-439        GifStyleEncoder
+//   lzw/src/encoder.rs:479-487, 519-523        TiffStyleEncoder
+//   lzw/src/encoder.rs:565-576, 609-616        FixedEncoder
+//   lzw/src/decoder.rs:99-120, 163-172         VariableDecoder::{decode, decode_to_vec}
+//   lzw/src/decoder.rs:333-340, 378-382        GifStyleDecoder
+//   lzw/src/decoder.rs:420-428, 460-464        TiffStyleDecoder
+//   lzw/src/decoder.rs:503-514, 544-551        FixedDecoder
+// `R: Read` becomes anything with data()/size() of bytes or a std::istream, `W: Write` a
+// std::ostream or a std::vector<uint8_t>; `Result<_, E>` becomes an exception of type E thrown
+// AFTER the bytes produced before the error have reached the writer, as in the reference.
+// New relative to the reference: encode_batch / decode_batch (many independent streams per call).
+// There is no CPU path: the first call on a machine without an sm_100 GPU throws std::runtime_error.
+#ifndef SALZWEG_HPP
+#define SALZWEG_HPP
+
+#include <cstdint>
+#include <istream>
+#include <iterator>
+#include <ostream>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "slzw.h"
+
+namespace salzweg {
+
+/// lzw/src/lib.rs:59-65
+enum class Endianness { BigEndian, LittleEndian };
+
+/// lzw/src/lib.rs:71-91
+enum class CodeSizeStrategy { Default, Tiff };
+inline uint16_t increment(CodeSizeStrategy s) { return s == CodeSizeStrategy::Tiff ? 1 : 0; }
+
+namespace detail {
+
+inline std::string message(bool decoder, uint32_t status, uint32_t det, uint8_t code_size) {
+    char buf[160];
+    slzw_status_message(decoder ? 1 : 0, status, det, code_size, buf, sizeof buf);
+    return buf;
+}
+
+// one context per thread: the reference's functions are stateless and re-entrant
+inline slzw_ctx* context() {
+    struct Holder {
+        slzw_ctx* ctx = nullptr;
+        Holder() {
+            const int rc = slzw_create(0, &ctx);
+            if (rc != SLZW_RC_OK)
+                throw std::runtime_error(rc == SLZW_RC_NO_DEVICE
+                                             ? "salzweg (B200): no usable sm_100 CUDA device, and there is no CPU path"
+                                             : "salzweg (B200): slzw_create failed");
+        }
+        ~Holder() { slzw_destroy(ctx); }
+    };
+    thread_local Holder h;
+    return h.ctx;
+}
+
+inline slzw_params params(uint8_t flavour, uint8_t code_size, Endianness e, CodeSizeStrategy s) {
+    slzw_params p;
+    p.flavour = flavour;
+    p.code_size = code_size;
+    p.big_endian = e == Endianness::BigEndian ? 1 : 0;
+    p.tiff_early_change = s == CodeSizeStrategy::Tiff ? 1 : 0;
+    return p;
+}
+
+inline std::vector<uint8_t> read_all(std::istream& in) {
+    return std::vector<uint8_t>(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+}
+
+struct VecWriter {
+    std::vector<uint8_t>& v;
+    void write_all(const uint8_t* p, size_t n) { v.insert(v.end(), p, p + n); }
+};
+struct StreamWriter {
+    std::ostream& s;
+    void write_all(const uint8_t* p, size_t n) { s.write(reinterpret_cast<const char*>(p), (std::streamsize)n); }
+};
+
+}  // namespace detail
+
+/// lzw/src/encoder.rs:16-29; what() is the reference's Display text (encoder.rs:31-44)
+struct EncodingError : std::runtime_error {
+    enum class Kind { Io, CodeSize, UnexpectedCode };
+    Kind kind;
+    uint8_t code = 0, code_size = 0;  // CodeSize(code_size) / UnexpectedCode{code, code_size}
+    uint32_t status = 0;              // slzw_status (Io: UnexpectedEof or WriteZero)
+    EncodingError(Kind k, uint32_t st, uint32_t det, uint8_t cs)
+        : std::runtime_error(detail::message(false, st, det, cs)), kind(k), status(st) {
+        if (k == Kind::CodeSize) code_size = (uint8_t)det;
+        if (k == Kind::UnexpectedCode) {
+            code = (uint8_t)det;
+            code_size = cs;
+        }
+    }
+};
+
+/// lzw/src/decoder.rs:15-25; what() is the reference's Display text (decoder.rs:27-42)
+struct DecodingError : std::runtime_error {
+    enum class Kind { Io, CodeSize, UnexpectedCode, MissingClearCode };
+    Kind kind;
+    uint16_t code = 0;     // UnexpectedCode(code)
+    uint8_t code_size = 0; // CodeSize(code_size)
+    uint32_t status = 0;
+    DecodingError(Kind k, uint32_t st, uint32_t det)
+        : std::runtime_error(detail::message(true, st, det, 0)), kind(k), status(st) {
+        if (k == Kind::UnexpectedCode) code = (uint16_t)det;
+        if (k == Kind::CodeSize) code_size = (uint8_t)det;
+    }
+};
+
+namespace detail {
+
+[[noreturn]] inline void launch_failure(const char* what) {
+    throw std::runtime_error(std::string(what) + ": " + slzw_last_error(context()));
+}
+
+inline void throw_encoding(uint32_t st, uint32_t det, uint8_t cs) {
+    switch (st) {
+        case SLZW_ERR_CODE_SIZE: throw EncodingError(EncodingError::Kind::CodeSize, st, det, cs);
+        case SLZW_ERR_UNEXPECTED_CODE: throw EncodingError(EncodingError::Kind::UnexpectedCode, st, det, cs);
+        case SLZW_ERR_REFERENCE_PANIC:
+            throw std::out_of_range("index out of bounds (salzweg panics on this input, encoder.rs:99)");
+        default: throw EncodingError(EncodingError::Kind::Io, st, det, cs);
+    }
+}
+
+inline void throw_decoding(uint32_t st, uint32_t det) {
+    switch (st) {
+        case SLZW_ERR_CODE_SIZE: throw DecodingError(DecodingError::Kind::CodeSize, st, det);
+        case SLZW_ERR_UNEXPECTED_CODE: throw DecodingError(DecodingError::Kind::UnexpectedCode, st, det);
+        case SLZW_ERR_MISSING_CLEAR_CODE: throw DecodingError(DecodingError::Kind::MissingClearCode, st, det);
+        case SLZW_ERR_REFERENCE_PANIC:
+            throw std::out_of_range("index out of bounds (salzweg panics on this input, decoder.rs:247)");
+        default: throw DecodingError(DecodingError::Kind::Io, st, det);
+    }
+}
+
+template <class W>
+void run_encode(const uint8_t* data, size_t n, W into, const slzw_params& p) {
+    std::vector<uint8_t> out(slzw_encode_bound(&p, n));
+    uint64_t len = 0;
+    uint32_t det = 0;
+    const int st = slzw_encode(context(), &p, data, n, out.data(), out.size(), &len, &det);
+    if (st < 0) launch_failure("slzw_encode");
+    into.write_all(out.data(), (size_t)len);  // bytes produced before an error stay written
+    if (st != SLZW_OK) throw_encoding((uint32_t)st, det, p.code_size);
+}
+
+template <class W>
+void run_decode(const uint8_t* data, size_t n, W into, const slzw_params& p) {
+    uint64_t len = 0;
+    uint32_t det = 0;
+    int st = slzw_decode(context(), &p, data, n, nullptr, 0, &len, &det);  // size-only pass
+    if (st < 0) launch_failure("slzw_decode");
+    std::vector<uint8_t> out((size_t)len ? (size_t)len : 1);
+    st = slzw_decode(context(), &p, data, n, out.data(), len, &len, &det);
+    if (st < 0) launch_failure("slzw_decode");
+    into.write_all(out.data(), (size_t)len);
+    if (st != SLZW_OK) throw_decoding((uint32_t)st, det);
+}
+
+// The four codecs differ only in how their arguments map to slzw_params; ENC selects the direction.
+template <bool ENC, class W>
+void run(const uint8_t* data, size_t n, W into, const slzw_params& p) {
+    if (ENC) run_encode(data, n, into, p);
+    else run_decode(data, n, into, p);
+}
+
+// Argument adapters shared by every type: (bytes | istream) x (ostream | vector) and *_to_vec.
+template <bool ENC, class Data, class Into>
+void dispatch(Data& data, Into& into, const slzw_params& p) {
+    using D = std::remove_cv_t<std::remove_reference_t<Data>>;
+    using I = std::remove_cv_t<std::remove_reference_t<Into>>;
+    if constexpr (std::is_base_of_v<std::istream, D>) {
+        const std::vector<uint8_t> bytes = read_all(data);
+        dispatch<ENC>(bytes, into, p);
+    } else if constexpr (std::is_base_of_v<std::ostream, I>) {
+        run<ENC>(reinterpret_cast<const uint8_t*>(data.data()), data.size(), StreamWriter{into}, p);
+    } else {
+        static_assert(std::is_same_v<I, std::vector<uint8_t>>, "into: std::ostream or std::vector<uint8_t>");
+        run<ENC>(reinterpret_cast<const uint8_t*>(data.data()), data.size(), VecWriter{into}, p);
+    }
+}
+template <bool ENC, class Data>
+std::vector<uint8_t> to_vec(Data& data, const slzw_params& p) {
+    std::vector<uint8_t> v;
+    dispatch<ENC>(data, v, p);  // like the reference, the partially filled Vec is dropped with the error
+    return v;
+}
+
+}  // namespace detail
+
+// ---- encoders --------------------------------------------------------------------------------------
+struct VariableEncoder {
+    template <class R, class W>
+    static void encode(R&& data, W&& into, uint8_t code_size, Endianness endianness, CodeSizeStrategy strategy) {
+        detail::dispatch<true>(data, into, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
+    }
+    template <class R>
+    static std::vector<uint8_t> encode_to_vec(R&& data, uint8_t code_size, Endianness endianness,
+                                              CodeSizeStrategy strategy) {
+        return detail::to_vec<true>(data, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
+    }
+};
+
+struct GifStyleEncoder {
+    template <class R, class W>
+    static void encode(R&& data, W&& into, uint8_t code_size) {
+        VariableEncoder::encode(data, into, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
+    }
+    template <class R>
+    static std::vector<uint8_t> encode_to_vec(R&& data, uint8_t code_size) {
+        return VariableEncoder::encode_to_vec(data, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
+    }
+};
+
+struct TiffStyleEncoder {
+    template <class R, class W>
+    static void encode(R&& data, W&& into) {
+        VariableEncoder::encode(data, into, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
+    }
+    template <class R>
+    static std::vector<uint8_t> encode_to_vec(R&& data) {
+        return VariableEncoder::encode_to_vec(data, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
+    }
+};
+
+struct FixedEncoder {
+    template <class R, class W>
+    static void encode(R&& data, W&& into, Endianness endianness) {
+        detail::dispatch<true>(data, into, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
+    }
+    template <class R>
+    static std::vector<uint8_t> encode_to_vec(R&& data, Endianness endianness) {
+        return detail::to_vec<true>(data, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
+    }
+};
+
+// ---- decoders --------------------------------------------------------------------------------------
+struct VariableDecoder {
+    template <class R, class W>
+    static void decode(R&& data, W&& into, uint8_t code_size, Endianness endianness, CodeSizeStrategy strategy) {
+        detail::dispatch<false>(data, into, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
+    }
+    template <class R>
+    static std::vector<uint8_t> decode_to_vec(R&& data, uint8_t code_size, Endianness endianness,
+                                              CodeSizeStrategy strategy) {
+        return detail::to_vec<false>(data, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
+    }
+};
+
+struct GifStyleDecoder {
+    template <class R, class W>
+    static void decode(R&& data, W&& into, uint8_t code_size) {
+        VariableDecoder::decode(data, into, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
+    }
+    template <class R>
+    static std::vector<uint8_t> decode_to_vec(R&& data, uint8_t code_size) {
+        return VariableDecoder::decode_to_vec(data, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
+    }
+};
+
+struct TiffStyleDecoder {
+    template <class R, class W>
+    static void decode(R&& data, W&& into) {
+        VariableDecoder::decode(data, into, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
+    }
+    template <class R>
+    static std::vector<uint8_t> decode_to_vec(R&& data) {
+        return VariableDecoder::decode_to_vec(data, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
+    }
+};
+
+struct FixedDecoder {
+    template <class R, class W>
+    static void decode(R&& data, W&& into, Endianness endianness) {
+        detail::dispatch<false>(data, into, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
+    }
+    template <class R>
+    static std::vector<uint8_t> decode_to_vec(R&& data, Endianness endianness) {
+        return detail::to_vec<false>(data, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
+    }
+};
+
+// ---- batches (new relative to the reference) --------------------------------------------------------
+/// One stream's outcome of a batched call: the bytes produced (also those before an error) and the
+/// status / detail of include/slzw.h (0 = ok).
+struct StreamResult {
+    std::vector<uint8_t> bytes;
+    uint32_t status = 0, detail = 0;
+    bool ok() const { return status == SLZW_OK; }
+};
+
+/// Encodes streams data[offsets[i] .. offsets[i+1]) with one configuration; per-stream code sizes
+/// (GIF frames with different palettes) may be given in `code_sizes`.
+inline std::vector<StreamResult> encode_batch(const uint8_t* data, const std::vector<uint64_t>& offsets,
+                                              uint8_t flavour, uint8_t code_size, Endianness endianness,
+                                              CodeSizeStrategy strategy,
+                                              const std::vector<uint8_t>* code_sizes = nullptr) {
+    const slzw_params p = detail::params(flavour, code_size, endianness, strategy);
+    const uint64_t n = offsets.empty() ? 0 : offsets.size() - 1;
+    std::vector<StreamResult> res(n);
+    if (n == 0) return res;
+    std::vector<uint64_t> out_off(n + 1, 0), len(n);
+    for (uint64_t i = 0; i < n; i++)
+        out_off[i + 1] = out_off[i] + ((slzw_encode_bound(&p, offsets[i + 1] - offsets[i]) + 15) & ~15ull);
+    std::vector<uint8_t> out(out_off[n] ? out_off[n] : 1);
+    std::vector<uint32_t> st(n), det(n);
+    slzw_batch b{data, offsets.data(), out.data(), out_off.data(), len.data(), st.data(), det.data(),
+                 code_sizes ? code_sizes->data() : nullptr, n};
+    if (slzw_encode_batch_host(detail::context(), &p, &b) != SLZW_RC_OK) detail::launch_failure("slzw_encode_batch_host");
+    for (uint64_t i = 0; i < n; i++) {
+        res[i].bytes.assign(out.begin() + out_off[i], out.begin() + out_off[i] + len[i]);
+        res[i].status = st[i];
+        res[i].detail = det[i];
+    }
+    return res;
+}
+
+/// Decodes streams data[offsets[i] .. offsets[i+1]); capacities[i] is the room given to stream i
+/// (the analogue of a `&mut [u8]` writer, e.g. the strip size of a TIFF).
+inline std::vector<StreamResult> decode_batch(const uint8_t* data, const std::vector<uint64_t>& offsets,
+                                              const std::vector<uint64_t>& capacities, uint8_t flavour,
+                                              uint8_t code_size, Endianness endianness, CodeSizeStrategy strategy,
+                                              const std::vector<uint8_t>* code_sizes = nullptr) {
+    const slzw_params p = detail::params(flavour, code_size, endianness, strategy);
+    const uint64_t n = offsets.empty() ? 0 : offsets.size() - 1;
+    std::vector<StreamResult> res(n);
+    if (n == 0) return res;
+    std::vector<uint64_t> out_off(n + 1, 0), len(n);
+    for (uint64_t i = 0; i < n; i++) out_off[i + 1] = out_off[i] + capacities[i];
+    std::vector<uint8_t> out(out_off[n] ? out_off[n] : 1);
+    std::vector<uint32_t> st(n), det(n);
+    slzw_batch b{data, offsets.data(), out.data(), out_off.data(), len.data(), st.data(), det.data(),
+                 code_sizes ? code_sizes->data() : nullptr, n};
+    if (slzw_decode_batch_host(detail::context(), &p, &b) != SLZW_RC_OK) detail::launch_failure("slzw_decode_batch_host");
+    for (uint64_t i = 0; i < n; i++) {
+        res[i].bytes.assign(out.begin() + out_off[i], out.begin() + out_off[i] + len[i]);
+        res[i].status = st[i];
+        res[i].detail = det[i];
+    }
+    return res;
+}
+
+}  // namespace salzweg
+
+#endif  // SALZWEG_HPP
