@@ -1,14 +1,17 @@
-"""CPU model of slzw_decode_fast_kernel's step algorithm (decode_kernels.cu), checked against the
-oracle.  Debug aid: it mirrors the kernel's per-step logic (32 codes per step, classification,
-in-step length resolution, word-start bit mask, source-pointer following) with plain Python so
-that the algorithm can be validated without a GPU.  Not part of the product."""
+"""CPU model of slzw_decode_fast_kernel's step algorithm (lzw_b200/csrc/decode_kernels.cu).
+
+It mirrors the kernel's per-step logic (32 codes per step, classification, in-step length
+resolution, word-start bit mask, source-pointer following, deferral rules) in plain Python, so
+that the algorithm -- not the CUDA -- can be checked against the oracle without a GPU
+(tests/test_fast_decode_model.py).  Test infrastructure, not part of the product."""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 from tests import cases as T    # noqa: E402
 
