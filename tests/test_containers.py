@@ -119,3 +119,61 @@ def test_gpu_tiff_strips_decode_with_libtiff():
             assert np.array_equal(dec[: buf.size], buf)
     finally:
         codec.close()
+
+
+# ---- streams written by other encoders ---------------------------------------------------------------
+def _pil_gif(px, palette):
+    im = Image.fromarray(px, mode="P")
+    im.putpalette([c for rgb in palette for c in rgb])
+    b = io.BytesIO()
+    im.save(b, format="GIF", interlace=False)
+    data = b.getvalue()
+    return data, np.asarray(Image.open(io.BytesIO(data)))
+
+
+def _libtiff_tiff(rgb):
+    b = io.BytesIO()
+    Image.fromarray(rgb).save(b, format="TIFF", compression="tiff_lzw")
+    return b.getvalue()
+
+
+def test_oracle_decodes_streams_of_other_encoders():
+    """The reference's decoder semantics (the oracle) read what PIL's GIF encoder and libtiff's LZW
+    encoder write (libtiff widens the code before the end-of-information code where salzweg's
+    encoder does not -- SURVEY F1 -- which is exactly what salzweg's decoder expects)."""
+    px, palette = _tokyo()
+    data, want = _pil_gif(px, palette)
+    (w, h, mcs, stream), = K.read_gif_frames(data)
+    st, _, out = O.decode(O.gif(mcs), stream, cap=w * h)
+    assert st == 0 and np.array_equal(np.frombuffer(out, dtype=np.uint8).reshape(h, w), want)
+    rgb = _sunflower()
+    w, h, spp, rps, strips = K.read_tiff_strips(_libtiff_tiff(rgb))
+    raw, pos = rgb.tobytes(), 0
+    for i, s in enumerate(strips):
+        n = min(rps, h - i * rps) * w * spp
+        st, _, out = O.decode(O.tiff(), s, cap=n)
+        assert st == 0 and out == raw[pos:pos + n], i
+        pos += n
+
+
+@pytest.mark.gpu
+def test_gpu_decodes_streams_of_other_encoders():
+    import lzw_b200
+    from lzw_b200.types import gif_params, tiff_params
+    codec = lzw_b200.Codec(0)
+    try:
+        px, palette = _tokyo()
+        data, want = _pil_gif(px, palette)
+        (w, h, mcs, stream), = K.read_gif_frames(data)
+        st, det, out = codec.decode(gif_params(mcs), stream, cap=w * h)
+        assert (st, det) == (0, 0) and np.array_equal(np.frombuffer(out, dtype=np.uint8).reshape(h, w), want)
+        rgb = _sunflower()
+        w, h, spp, rps, strips = K.read_tiff_strips(_libtiff_tiff(rgb))
+        in_off = np.zeros(len(strips) + 1, dtype=np.uint64)
+        in_off[1:] = np.cumsum([len(s) for s in strips])
+        caps = np.zeros(len(strips) + 1, dtype=np.uint64)
+        caps[1:] = np.cumsum([min(rps, h - i * rps) * w * spp for i in range(len(strips))])
+        dec, dlen, dst, _ = codec.decode_batch(tiff_params(), np.frombuffer(b"".join(strips), dtype=np.uint8), in_off, caps)
+        assert (dst == 0).all() and dec[: rgb.size].tobytes() == rgb.tobytes()
+    finally:
+        codec.close()
