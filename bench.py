@@ -353,9 +353,18 @@ def run_ours(args):
     # ---- end to end through the host-buffer C ABI (pinned host memory) ----
     e2e = None
     if not args.no_e2e:
-        h_in = torch.from_numpy(buf).pin_memory().numpy()
-        h_dense = torch.empty(int(slots[-1]), dtype=torch.uint8).pin_memory().numpy()
-        h_dec = torch.empty(total, dtype=torch.uint8).pin_memory().numpy()
+        # device memory of the kernel-only measurement is no longer needed
+        del t_in, t_enc, t_dense, t_dec
+        torch.cuda.empty_cache()
+        dense_cap = comp_total + comp_total // 64 + (1 << 20)  # the compressed size is known by now
+        pinned = True
+        try:
+            h_in = torch.from_numpy(buf).pin_memory().numpy()
+            h_dense = torch.empty(dense_cap, dtype=torch.uint8).pin_memory().numpy()
+            h_dec = torch.empty(total, dtype=torch.uint8).pin_memory().numpy()
+        except RuntimeError:  # the host cannot page-lock this much: pageable buffers, copies are staged
+            pinned = False
+            h_in, h_dense, h_dec = buf, np.empty(dense_cap, dtype=np.uint8), np.empty(total, dtype=np.uint8)
         e2e_steps = max(1, min(args.steps, 3))
         h2d = d2h = 0
         # one untimed pass: staging buffers of the host path are allocated on first use
@@ -376,7 +385,7 @@ def run_ours(args):
         dt = float(te.item())
         e2e = {"value": world * total * e2e_steps / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
-               "steps": e2e_steps, "round_trip_ok": bool(np.array_equal(dec[:total], buf)),
+               "steps": e2e_steps, "round_trip_ok": bool(np.array_equal(dec[:total], buf)), "pinned": pinned,
                "note": "slzw_encode_batch_host_dense + slzw_decode_batch_host on pinned host buffers; the "
                        "encoder reads its pinned input in place over PCIe (counted in h2d_bytes_per_step), "
                        "everything else is cudaMemcpyAsync inside the call"}

@@ -4,6 +4,7 @@
 // the sm_100a kernels of encode_kernels.cu / decode_kernels.cu / sched_kernels.cu and returns
 // SLZW_RC_NO_DEVICE / SLZW_RC_CUDA when that is impossible.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -172,6 +173,13 @@ bool params_ok(const slzw_params* p) {
     return p && (p->flavour == SLZW_FLAVOUR_VARIABLE || p->flavour == SLZW_FLAVOUR_FIXED);
 }
 
+// NVTX range around a phase of a call (visible in Nsight Systems timelines; header-only, a no-op
+// when no tool is attached).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // Picks a workspace, makes `stream` wait for its previous user, builds the processing order.
 int prepare(slzw_ctx* ctx, const uint64_t* d_in_off, uint64_t n, cudaStream_t stream,
             Workspace** out_ws) {
@@ -230,6 +238,8 @@ enum class Op { Encode, Decode, DecodedSizes };
 int run_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, cudaStream_t stream,
                Op op) {
     if (!ctx) return SLZW_RC_INVALID;
+    NvtxRange range(op == Op::Encode ? "slzw encode batch (device)"
+                                     : op == Op::Decode ? "slzw decode batch (device)" : "slzw decoded sizes (device)");
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (!params_ok(params) || !b) {
         snprintf(ctx->err, sizeof ctx->err, "invalid params or batch");
@@ -345,6 +355,7 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
         snprintf(ctx->err, sizeof ctx->err, "invalid batch (null pointer)");
         return SLZW_RC_INVALID;
     }
+    NvtxRange range(op == Op::Encode ? "slzw encode batch (host pipeline)" : "slzw decode batch (host pipeline)");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
     // chunk by the larger side of the stream (uncompressed bytes)
@@ -447,6 +458,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     if (needed) *needed = 0;
     if (n == 0) return SLZW_RC_OK;
     if (align == 0) align = 1;
+    NvtxRange range("slzw encode batch, dense (host pipeline)");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
     const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->enc_chunk_bytes);
