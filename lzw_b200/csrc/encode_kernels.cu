@@ -71,7 +71,7 @@ struct EncMisc {
     static constexpr int kRecs = TILE + 8;                      // + lookahead padding
     static constexpr int kCodeBuf = TILE + 16;                  // codes one tile can emit
     static constexpr int kOutWords = (kCodeBuf * 12) / 32 + 4;  // packed window
-    uint2 rec[kRecs];          // per input byte: {byte << 12, hash bits | table base}
+    alignas(16) uint2 rec[kRecs];  // per input byte: {byte << 12, hash bits | table base}
     uint32_t outw[kOutWords];
     uint16_t codes[kCodeBuf];  // [width:4 | code':12]
 };
@@ -434,7 +434,9 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
         }
     } else if constexpr (U >= 2) {
         while (i + 2u <= len) {
-            const uint2 r0 = rec[i], r1 = rec[i + 1];
+            // two records with one 128-bit load (i is even, rec is 16-byte aligned)
+            const uint4 rr = *reinterpret_cast<const uint4*>(rec + i);
+            const uint2 r0 = make_uint2(rr.x, rr.y), r1 = make_uint2(rr.z, rr.w);
             SLZW_STEP_B(r0)
             SLZW_STEP_B(r1)
             i += 2u;
