@@ -217,6 +217,32 @@ def run_reference(args):
     }))
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Runs this process on the CPUs of the NUMA node the GPU hangs off, so that the pinned host
+    buffers of the end-to-end path (first touched after this call) are local to it.  Matters when
+    several ranks share one host; returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    return None
+
+
 # ---- our arm ---------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -232,6 +258,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; lzw_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -386,6 +413,7 @@ def run_ours(args):
         e2e = {"value": world * total * e2e_steps / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                "steps": e2e_steps, "round_trip_ok": bool(np.array_equal(dec[:total], buf)), "pinned": pinned,
+               "numa_node_rank0": numa_node,
                "note": "slzw_encode_batch_host_dense + slzw_decode_batch_host on pinned host buffers; the "
                        "encoder reads its pinned input in place over PCIe (counted in h2d_bytes_per_step), "
                        "everything else is cudaMemcpyAsync inside the call"}
