@@ -97,6 +97,11 @@ typedef struct slzw_params {
 
 #define SLZW_FLAVOUR_VARIABLE 0
 #define SLZW_FLAVOUR_FIXED 1
+/* Extension, decoders only: flavour 0, except that a full dictionary is not an
+ * error -- the decoder keeps decoding with the 4096 entries it has until a clear code arrives
+ * ("deferred clear", which GIF encoders other than salzweg's may use), instead of returning
+ * MissingClearCode (decoder.rs:281-283).  Encoders treat it as flavour 0. */
+#define SLZW_FLAVOUR_VARIABLE_LENIENT 2
 
 /* ---- a batch of independent streams -----------------------------------------------------
  * Stream i reads in[in_off[i] .. in_off[i+1]) and may write out[out_off[i] .. out_off[i+1])

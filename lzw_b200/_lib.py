@@ -29,6 +29,7 @@ RC_NOMEM = -4
 
 FLAVOUR_VARIABLE = 0
 FLAVOUR_FIXED = 1
+FLAVOUR_VARIABLE_LENIENT = 2
 
 
 class Params(C.Structure):

@@ -66,6 +66,7 @@ __device__ void decode_stream_exact(const DevBatch& a, uint32_t sid, DecWarpSmem
         cap = a.out_off[sid + 1] - ob;
     }
     const bool fixed = a.p.flavour == SLZW_FLAVOUR_FIXED;
+    const bool lenient = a.p.flavour == SLZW_FLAVOUR_VARIABLE_LENIENT;  // full table freezes, no error
     const bool big = a.p.big_endian != 0;
     const uint32_t inc = (!fixed && a.p.tiff_early_change) ? 1u : 0u;
     const uint32_t cs = fixed ? 8u : (a.code_size ? a.code_size[sid] : a.p.code_size);
@@ -147,7 +148,7 @@ __device__ void decode_stream_exact(const DevBatch& a, uint32_t sid, DecWarpSmem
                             read_size++;
                             mask = (1u << read_size) - inc;
                         }
-                    } else if (!fixed) {
+                    } else if (!fixed && !lenient) {
                         status = SLZW_ERR_MISSING_CLEAR_CODE;
                         break;
                     }
@@ -352,6 +353,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, uint32_t* __
         if (cap >= 0x80000000ull) return false;  // offsets are 31 bits + literal flag
     }
     const bool fixed = a.p.flavour == SLZW_FLAVOUR_FIXED;
+    const bool lenient = a.p.flavour == SLZW_FLAVOUR_VARIABLE_LENIENT;  // full table freezes, no error
     const bool big = a.p.big_endian != 0;
     const uint32_t inc = (!fixed && a.p.tiff_early_change) ? 1u : 0u;
     const uint32_t cs = fixed ? 8u : (a.code_size ? a.code_size[sid] : a.p.code_size);
@@ -396,7 +398,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, uint32_t* __
         }
         uint32_t bmax = avail < 32u ? avail : 32u;
         const uint32_t adj = hp ? 0u : 1u;   // the first code after a clear creates no entry
-        if (!(fixed && nidx >= (uint32_t)kMaxTable)) {
+        if (!((fixed || lenient) && nidx >= (uint32_t)kMaxTable)) {
             const uint32_t room = (w < 12u ? mask : (uint32_t)kMaxTable) - nidx + adj;
             if (room < bmax) bmax = room;
         }
@@ -526,7 +528,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, uint32_t* __
                 else if (qd == -1) srci = prev_off;
             }
             // offsets of this step's entries must fit the entry format
-            if (dst && !(fixed && nidx >= (uint32_t)kMaxTable) && produced + total - seg_base >= kFastMaxSpan)
+            if (dst && !((fixed || lenient) && nidx >= (uint32_t)kMaxTable) && produced + total - seg_base >= kFastMaxSpan)
                 return false;
             // ---- new entries (decoder.rs:272-276 / 630-634) ----
             {
@@ -624,7 +626,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, uint32_t* __
             produced += total;
             produced64 += total;
             bitpos += (uint64_t)b * w;  // all codes of the step were read at the width before a bump
-            if (!(fixed && nidx >= (uint32_t)kMaxTable)) {
+            if (!((fixed || lenient) && nidx >= (uint32_t)kMaxTable)) {
                 nidx += b - adj;
                 if (!fixed && nidx == mask && w < 12u) {  // decoder.rs:277-280
                     w++;

@@ -170,7 +170,8 @@ struct DeviceGuard {
 };
 
 bool params_ok(const slzw_params* p) {
-    return p && (p->flavour == SLZW_FLAVOUR_VARIABLE || p->flavour == SLZW_FLAVOUR_FIXED);
+    return p && (p->flavour == SLZW_FLAVOUR_VARIABLE || p->flavour == SLZW_FLAVOUR_FIXED ||
+                 p->flavour == SLZW_FLAVOUR_VARIABLE_LENIENT);
 }
 
 // NVTX range around a phase of a call (visible in Nsight Systems timelines; header-only, a no-op

@@ -36,3 +36,9 @@ def tiff_params() -> _lib.Params:
 def fixed_params(endianness: Endianness) -> _lib.Params:
     """encoder.rs:565-576 / decoder.rs:503-514"""
     return _lib.Params(_lib.FLAVOUR_FIXED, 0, endianness.value, 0)
+
+
+def lenient_params(code_size: int, endianness: Endianness, strategy: CodeSizeStrategy) -> _lib.Params:
+    """Decoder extension (include/slzw.h, SLZW_FLAVOUR_VARIABLE_LENIENT): like variable_params, but a
+    full dictionary freezes until the next clear code instead of raising MissingClearCode."""
+    return _lib.Params(_lib.FLAVOUR_VARIABLE_LENIENT, code_size & 0xFF, endianness.value, strategy.value)

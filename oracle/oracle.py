@@ -69,6 +69,11 @@ def variable(code_size: int, big_endian: bool, tiff_early_change: bool) -> Param
     return Params(0, code_size, 1 if big_endian else 0, 1 if tiff_early_change else 0)
 
 
+def lenient(code_size: int, big_endian: bool = False, tiff_early_change: bool = False) -> Params:
+    """Extension of include/slzw.h (not in the reference): a full dictionary freezes, no MissingClearCode."""
+    return Params(2, code_size, 1 if big_endian else 0, 1 if tiff_early_change else 0)
+
+
 def build(force: bool = False) -> str:
     """Compile liboracle.so with the committed Makefile (building the checker is not using it)."""
     src = os.path.join(_HERE, "slzw_oracle.c")

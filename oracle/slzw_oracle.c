@@ -391,8 +391,10 @@ typedef struct {
     uint8_t decoding_stack[MAX_STACK_SIZE];
 } dec_tables_t;
 
+/* `lenient` is NOT in the reference: it restates include/slzw.h's SLZW_FLAVOUR_VARIABLE_LENIENT
+ * (a full dictionary freezes instead of failing) so that the extension has a checker too. */
 static int variable_decode(src_t* data, sink_t* into, uint8_t code_size, int big, int tiff,
-                           uint32_t* detail, dec_tables_t* t) {
+                           int lenient, uint32_t* detail, dec_tables_t* t) {
     const uint8_t MAX_READ_SIZE = 12;
     *detail = 0;
     if (!(code_size >= 2 && code_size <= 8)) { /* 180-182 */
@@ -479,7 +481,7 @@ static int variable_decode(src_t* data, sink_t* into, uint8_t code_size, int big
                 read_size += 1;
                 size_increase_mask = (uint16_t)((1u << read_size) - increment);
             }
-        } else {
+        } else if (!lenient) {
             return SLZW_ERR_MISSING_CLEAR_CODE; /* 281-283 */
         }
         previous_code = initial_code; /* 284 */
@@ -598,7 +600,8 @@ ORACLE_API int oracle_decode(const slzw_params* params, const uint8_t* in, uint6
         st = fixed_decode(&src, &sink, params->big_endian != 0, &d, t);
     else
         st = variable_decode(&src, &sink, params->code_size, params->big_endian != 0,
-                             params->tiff_early_change != 0, &d, t);
+                             params->tiff_early_change != 0,
+                             params->flavour == SLZW_FLAVOUR_VARIABLE_LENIENT, &d, t);
     free(t);
     if (out_len) *out_len = sink.len;
     if (detail) *detail = d;
@@ -647,7 +650,8 @@ static void* batch_worker(void* arg) {
                     st = fixed_decode(&src, &sink, p.big_endian != 0, &d, tabs);
                 else
                     st = variable_decode(&src, &sink, p.code_size, p.big_endian != 0,
-                                         p.tiff_early_change != 0, &d, tabs);
+                                         p.tiff_early_change != 0,
+                                         p.flavour == SLZW_FLAVOUR_VARIABLE_LENIENT, &d, tabs);
             } else {
                 if (p.flavour == SLZW_FLAVOUR_FIXED)
                     st = fixed_encode(&src, &sink, p.big_endian != 0, &d, tree);

@@ -177,3 +177,82 @@ def test_gpu_decodes_streams_of_other_encoders():
         assert (dst == 0).all() and dec[: rgb.size].tobytes() == rgb.tobytes()
     finally:
         codec.close()
+
+
+# ---- deferred clear codes: the opt-in lenient decoder flavour ----------------------
+def _gif_lzw_deferred_clear(pixels: bytes, cs: int) -> bytes:
+    """A GIF LZW encoder that never sends a clear code after the first one: once the dictionary has
+    4096 entries it keeps encoding with them (legal GIF, and what salzweg's own decoder rejects with
+    MissingClearCode, decoder.rs:281-283).  Plain Python, test input only."""
+    clear, eoi = 1 << cs, (1 << cs) + 1
+    table = {}
+    nxt, width = eoi + 1, cs + 1
+    acc = nbits = 0
+    out = bytearray()
+
+    def put(code):
+        nonlocal acc, nbits
+        acc |= code << nbits
+        nbits += width
+        while nbits >= 8:
+            out.append(acc & 0xFF)
+            acc >>= 8
+            nbits -= 8
+
+    put(clear)
+    prefix = pixels[0]
+    for k in pixels[1:]:
+        key = (prefix, k)
+        if key in table:
+            prefix = table[key]
+            continue
+        put(prefix)
+        if nxt < 4096:
+            table[key] = nxt
+            nxt += 1
+            if nxt > (1 << width) and width < 12:
+                width += 1
+        prefix = k
+    put(prefix)
+    put(eoi)
+    if nbits:
+        out.append(acc & 0xFF)
+    return bytes(out)
+
+
+def _deferred_clear_case():
+    rng = np.random.default_rng(11)
+    px = T.make_stream(rng, "walk", 300 * 200, 63).reshape(200, 300)     # fills the dictionary several times over
+    palette = [(4 * i, 255 - 4 * i, (7 * i) % 256) for i in range(64)]
+    stream = _gif_lzw_deferred_clear(px.tobytes(), 6)
+    return px, palette, stream
+
+
+def test_deferred_clear_stream_is_a_real_gif_and_the_oracle_modes_differ():
+    px, palette, stream = _deferred_clear_case()
+    im = Image.open(io.BytesIO(K.write_gif(300, 200, palette, [stream], 6)))
+    assert np.array_equal(np.asarray(im), px)                            # PIL's decoder defers, too
+    st, _, out = O.decode(O.gif(6), stream, cap=px.size)
+    assert st == O.ERR_MISSING_CLEAR_CODE and 0 < len(out) < px.size     # the reference's behaviour
+    st, det, out = O.decode(O.lenient(6), stream, cap=px.size)
+    assert (st, det) == (0, 0) and out == px.tobytes()
+
+
+@pytest.mark.gpu
+def test_gpu_lenient_flavour_decodes_deferred_clear_streams():
+    import lzw_b200
+    from lzw_b200.types import CodeSizeStrategy, Endianness, gif_params, lenient_params
+    codec = lzw_b200.Codec(0)
+    try:
+        px, palette, stream = _deferred_clear_case()
+        want = O.decode(O.gif(6), stream, cap=px.size)
+        assert codec.decode(gif_params(6), stream, cap=px.size) == want      # strict: MissingClearCode, same bytes
+        lp = lenient_params(6, Endianness.LittleEndian, CodeSizeStrategy.Default)
+        assert codec.decode(lp, stream, cap=px.size) == (0, 0, px.tobytes())
+        assert len(codec.last_deferred()) == 0                               # stays on the fast kernel
+        # ordinary streams decode the same in both flavours, and the exact kernel knows the flavour too
+        _, _, ok_stream = O.encode(O.gif(6), px.tobytes())
+        assert codec.decode(lp, ok_stream, cap=px.size) == (0, 0, px.tobytes())
+        assert codec.decode(lp, stream, cap=px.size // 2) == O.decode(O.lenient(6), stream, cap=px.size // 2)
+    finally:
+        codec.close()
