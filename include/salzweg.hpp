@@ -296,6 +296,22 @@ struct FixedDecoder {
     }
 };
 
+/// Extension (not in the reference): VariableDecoder that tolerates deferred clear codes -- a full
+/// dictionary freezes until the next clear code instead of raising MissingClearCode
+/// (SLZW_FLAVOUR_VARIABLE_LENIENT in slzw.h).
+struct LenientDecoder {
+    template <class R, class W>
+    static void decode(R&& data, W&& into, uint8_t code_size, Endianness endianness, CodeSizeStrategy strategy) {
+        detail::dispatch<false>(data, into,
+                                detail::params(SLZW_FLAVOUR_VARIABLE_LENIENT, code_size, endianness, strategy));
+    }
+    template <class R>
+    static std::vector<uint8_t> decode_to_vec(R&& data, uint8_t code_size, Endianness endianness,
+                                              CodeSizeStrategy strategy) {
+        return detail::to_vec<false>(data, detail::params(SLZW_FLAVOUR_VARIABLE_LENIENT, code_size, endianness, strategy));
+    }
+};
+
 // ---- batches (new relative to the reference) --------------------------------------------------------
 /// One stream's outcome of a batched call: the bytes produced (also those before an error) and the
 /// status / detail of include/slzw.h (0 = ok).
