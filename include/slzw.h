@@ -136,8 +136,8 @@ SLZW_API const char* slzw_last_error(const slzw_ctx* ctx);
 SLZW_API uint64_t slzw_kernel_launches(const slzw_ctx* ctx);
 SLZW_API uint32_t slzw_version(void);
 /* Diagnostics: the streams of the most recent decode call of this context that the fast decode
- * kernel handed to the exact-emulation kernel (malformed streams, full output slots, slots larger
- * than 1 MiB; see decode_kernels.cu).  Synchronises the device.  Returns their number and
+ * kernel handed to the exact-emulation kernel (malformed streams whose outcome depends on stale
+ * table state, more than 1 MiB of output between two clear codes; see decode_kernels.cu).  Synchronises the device.  Returns their number and
  * copies up to `cap` stream ids into `ids` (may be NULL).  After a *_host call that was split
  * into several chunks it describes the last chunk only (ids relative to that chunk). */
 SLZW_API uint64_t slzw_last_deferred(slzw_ctx* ctx, uint32_t* ids, uint64_t cap);

@@ -15,13 +15,14 @@
 // decoder.rs:244-250), a prefix sum of the word lengths, then a byte-parallel gather: every
 // output byte of the step finds its word through a bit mask of word starts, follows source
 // pointers that still point into the step itself, loads its byte from the stream's already
-// decoded output and stores it, coalesced.  Anything that is not the plain, successful case --
-// a code beyond the table, a missing clear code, input that ends before the end-of-information
-// code, a first code after a clear that is not a root (decoder.rs:230-236), a full output slot,
-// a word longer than the reference's stack, more than 1 MiB of output between two clear codes
-// (entries hold 20-bit offsets relative to the last clear) --
-// makes the kernel DEFER the stream: it is appended to a retry list and decoded again, from
-// scratch, by the exact kernel.
+// decoded output and stores it, coalesced.  Results identical to the reference are produced in the
+// kernel for success, input that ends before the end-of-information code (Io(UnexpectedEof)), a
+// code beyond the table (UnexpectedCode) and a full output slot (Io(WriteZero)).  Everything else
+// -- a missing clear code, a first code after a clear that is not a root (decoder.rs:230-236), a
+// word longer than the reference's stack, more than 1 MiB of output between two clear codes
+// (entries hold 20-bit offsets relative to the last clear), a slot of 1 GiB or more -- makes the
+// kernel DEFER the stream: it is appended to a retry list and decoded again, from scratch, by the
+// exact kernel.
 //
 // slzw_decode_exact_kernel -- reproduces VariableDecoder::inner_decode (decoder.rs:174-290) and
 // FixedDecoder::inner_decode (decoder.rs:553-642) state for state -- prefix/suffix/length
