@@ -194,6 +194,25 @@ SLZW_API int slzw_compact_device(slzw_ctx* ctx, const uint8_t* src, const uint64
                         const uint64_t* len, uint64_t n, uint64_t align, uint8_t* dst,
                         uint64_t* dst_off, void* cuda_stream);
 
+/* ---- TIFF Predictor = 2 (container step either side of the codec) --------
+ * Horizontal differencing of TIFF 6.0 section 14 for 8-bit samples, in place, on every strip of
+ * a batch: stream i occupies data[off[i] .. off[i] + len[i]) (len == NULL: up to off[i+1]) and is
+ * a sequence of rows of `row_bytes` bytes (ImageWidth * SamplesPerPixel; a short last row is
+ * allowed), samples_per_pixel in 1..4.  DIFFERENCE is what a writer applies before
+ * TiffStyleEncoder (lzw/src/encoder.rs:479-487) sees the strip, ACCUMULATE what a reader applies
+ * to TiffStyleDecoder's output (lzw/src/decoder.rs:420-428).  The reference has no counterpart:
+ * it stops at the code stream.  Device pointers, asynchronous on `cuda_stream`. */
+#define SLZW_PREDICTOR_DIFFERENCE 0
+#define SLZW_PREDICTOR_ACCUMULATE 1
+SLZW_API int slzw_tiff_predictor_device(slzw_ctx* ctx, int direction, uint8_t* data,
+                               const uint64_t* off, const uint64_t* len, uint64_t n,
+                               uint32_t row_bytes, uint32_t samples_per_pixel, void* cuda_stream);
+/* Makes the *_host batch entry points of this context apply the predictor on the device, inside
+ * their pipeline: encode calls difference the device copy of every input stream before encoding
+ * it (the caller's buffer is not modified), decode calls accumulate every decoded stream before it
+ * is copied back.  (0, 0) switches it off again (the default). */
+SLZW_API int slzw_set_tiff_predictor(slzw_ctx* ctx, uint32_t row_bytes, uint32_t samples_per_pixel);
+
 /* ---- helpers ----------------------------------------------------------------------------- */
 /* pinned host memory for the *_host entry points */
 SLZW_API void* slzw_host_alloc(size_t bytes);

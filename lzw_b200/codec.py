@@ -89,6 +89,24 @@ class Codec:
                                                   dst_ptr, dst_off_ptr, stream or None),
                     "slzw_compact_device")
 
+    # ---- TIFF Predictor = 2 (horizontal differencing, 8-bit samples) -------------------------
+    DIFFERENCE, ACCUMULATE = 0, 1
+
+    def tiff_predictor_device(self, direction, data_ptr, off_ptr, n, row_bytes, samples_per_pixel,
+                              len_ptr=0, stream=0):
+        """In place on device memory: stream i is data[off[i] .. off[i] + len[i]) (len_ptr == 0: up
+        to off[i + 1]), rows of row_bytes bytes."""
+        self._check(self._lib.slzw_tiff_predictor_device(self._h, direction, data_ptr, off_ptr,
+                                                         len_ptr or None, n, row_bytes,
+                                                         samples_per_pixel, stream or None),
+                    "slzw_tiff_predictor_device")
+
+    def set_tiff_predictor(self, row_bytes=0, samples_per_pixel=0):
+        """Host batch calls difference before encoding / accumulate after decoding, on the device.
+        (0, 0) switches the predictor off."""
+        self._check(self._lib.slzw_set_tiff_predictor(self._h, row_bytes, samples_per_pixel),
+                    "slzw_set_tiff_predictor")
+
     # ---- host-resident batches: numpy arrays -----------------------------------------------
     def _host(self, fn, params, in_buf, in_off, out_off, code_size, what, out=None):
         in_buf = np.ascontiguousarray(in_buf, dtype=np.uint8)

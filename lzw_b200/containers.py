@@ -105,9 +105,14 @@ def read_gif_frames(data: bytes):
 _TIFF_TYPES = {3: "H", 4: "I"}
 
 
-def write_tiff_lzw(width: int, height: int, samples_per_pixel: int, rows_per_strip: int, strips) -> bytes:
+def write_tiff_lzw(width: int, height: int, samples_per_pixel: int, rows_per_strip: int, strips,
+                   predictor: int = 1) -> bytes:
     """A little-endian baseline TIFF (8 bits per sample, chunky) whose strips are the given
-    TIFF-style LZW streams (Compression = 5, no predictor)."""
+    TIFF-style LZW streams (Compression = 5).  predictor = 2 records that the strips were
+    horizontally differenced before encoding (Codec.set_tiff_predictor / slzw_tiff_predictor_device
+    with row_bytes = width * samples_per_pixel)."""
+    if predictor not in (1, 2):
+        raise ValueError("TIFF predictor must be 1 (none) or 2 (horizontal differencing)")
     n = len(strips)
     if n != (height + rows_per_strip - 1) // rows_per_strip:
         raise ValueError("number of strips does not match height / rows_per_strip")
@@ -123,6 +128,8 @@ def write_tiff_lzw(width: int, height: int, samples_per_pixel: int, rows_per_str
     entries.append((278, 4, 1, [rows_per_strip]))
     entries.append((279, 4, n, [len(s) for s in strips]))
     entries.append((284, 3, 1, [1]))
+    if predictor == 2:
+        entries.append((317, 3, 1, [2]))
     ifd_offset = 8
     ifd_size = 2 + 12 * len(entries) + 4
     extra_offset = ifd_offset + ifd_size
@@ -162,9 +169,26 @@ def write_tiff_lzw(width: int, height: int, samples_per_pixel: int, rows_per_str
     return bytes(out)
 
 
+def read_tiff(data: bytes) -> dict:
+    """The first image of a TIFF file with Compression = 5 as a dict: width, height,
+    samples_per_pixel, rows_per_strip, predictor (1 or 2), strips (list of bytes).  The strips go to
+    TiffStyleDecoder / Codec.decode_batch; with predictor 2 the decoded strips still have to be
+    accumulated (Codec.set_tiff_predictor(width * samples_per_pixel, samples_per_pixel))."""
+    w, h, spp, rps, strips, predictor = _read_tiff(data)
+    return {"width": w, "height": h, "samples_per_pixel": spp, "rows_per_strip": rps,
+            "predictor": predictor, "strips": strips}
+
+
 def read_tiff_strips(data: bytes):
     """(width, height, samples_per_pixel, rows_per_strip, [strip bytes]) of the first image of a
-    TIFF file with Compression = 5; the strips go to TiffStyleDecoder / Codec.decode_batch."""
+    TIFF file with Compression = 5 and no predictor."""
+    w, h, spp, rps, strips, predictor = _read_tiff(data)
+    if predictor != 1:
+        raise ValueError("TIFF image uses a predictor: use read_tiff")
+    return w, h, spp, rps, strips
+
+
+def _read_tiff(data: bytes):
     if data[:2] == b"II":
         e = "<"
     elif data[:2] == b"MM":
@@ -186,11 +210,15 @@ def read_tiff_strips(data: bytes):
         tags[tag] = list(struct.unpack_from(fmt, data, off))
     if tags.get(259, [1])[0] != 5:
         raise ValueError("TIFF image is not LZW-compressed")
-    if tags.get(317, [1])[0] != 1:
-        raise ValueError("TIFF predictor is not supported")
+    predictor = tags.get(317, [1])[0]
+    if predictor not in (1, 2):
+        raise ValueError("TIFF predictor %d is not supported" % predictor)
+    if predictor == 2 and any(b != 8 for b in tags.get(258, [1])):
+        raise ValueError("TIFF predictor 2 is supported for 8-bit samples only")
     offs, counts = tags[273], tags[279]
     strips = [data[o:o + c] for o, c in zip(offs, counts)]
-    return tags[256][0], tags[257][0], tags.get(277, [1])[0], tags.get(278, [tags[257][0]])[0], strips
+    return (tags[256][0], tags[257][0], tags.get(277, [1])[0], tags.get(278, [tags[257][0]])[0], strips,
+            predictor)
 
 
 # ---- batches ---------------------------------------------------------------------------------------

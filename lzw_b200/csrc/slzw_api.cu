@@ -33,6 +33,9 @@ cudaError_t decode_fast_launch(const DevBatch& a, int num_sms, cudaStream_t stre
 int sched_size_classes();
 cudaError_t sched_build_order(const uint64_t* off, uint64_t n, uint32_t* hist, uint32_t* order,
                               int num_sms, cudaStream_t stream);
+cudaError_t predictor_launch(int direction, uint8_t* data, const uint64_t* off, const uint64_t* len,
+                             uint64_t n, uint32_t row_bytes, uint32_t spp, int num_sms,
+                             cudaStream_t stream);
 cudaError_t compact_launch(const uint8_t* src, const uint64_t* src_off, const uint64_t* len,
                            uint64_t n, uint64_t align, uint8_t* dst, uint64_t* dst_off, int num_sms,
                            cudaStream_t stream);
@@ -136,6 +139,9 @@ struct slzw_ctx {
     bool zero_copy_in = true;  // SLZW_HOST_ZERO_COPY=0 stages pinned input like pageable input
     uint64_t enc_chunk_bytes = kEncChunkBytes;
     uint64_t dec_chunk_bytes = kDecChunkBytes;
+    // TIFF Predictor = 2 applied by the host entry points (0 = off), slzw_set_tiff_predictor
+    uint32_t pred_row_bytes = 0;
+    uint32_t pred_spp = 0;
     uint64_t launches = 0;
     int last_decode_ws = -1;  // workspace of the most recent decode call
     char err[256] = {0};
@@ -366,7 +372,10 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
     const size_t chunks = cb.size() - 1;
     // encode: pinned input is read in place (the decoder's input is small and its access pattern
     // re-reads tiles, it stays staged)
-    const uint8_t* in_alias = (op == Op::Encode && ctx->zero_copy_in) ? device_alias(b->in) : nullptr;
+    // (not with the predictor, which rewrites the device copy of the input)
+    const bool predict = ctx->pred_row_bytes != 0 && needs_out;
+    const uint8_t* in_alias =
+        (op == Op::Encode && ctx->zero_copy_in && !predict) ? device_alias(b->in) : nullptr;
 
     auto enqueue = [&](size_t k) -> int {
         HostSlot& hs = ctx->pipe[k % kPipe];
@@ -410,8 +419,18 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
         d.detail = (uint32_t*)hs.detail.p;
         d.code_size = b->code_size ? (const uint8_t*)hs.cs.p : nullptr;
         d.n = m;
+        if (predict && op == Op::Encode) {
+            CK(predictor_launch(0, (uint8_t*)hs.in.p - in_lo, d.in_off, nullptr, m, ctx->pred_row_bytes,
+                                ctx->pred_spp, ctx->num_sms, s), "predictor launch");
+            ctx->launches += 1;
+        }
         int rc = run_device(ctx, params, &d, s, op);
         if (rc != SLZW_RC_OK) return rc;
+        if (predict && op == Op::Decode) {
+            CK(predictor_launch(1, d.out, d.out_off, d.out_len, m, ctx->pred_row_bytes, ctx->pred_spp,
+                                ctx->num_sms, s), "predictor launch");
+            ctx->launches += 1;
+        }
         if (needs_out && out_hi > out_lo)
             CK(cudaMemcpyAsync(b->out + out_lo, hs.out.p, out_hi - out_lo, cudaMemcpyDeviceToHost, s), "D2H out");
         CK(cudaMemcpyAsync(st.out_len, hs.out_len.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, s), "D2H out_len");
@@ -464,7 +483,9 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
     const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->enc_chunk_bytes);
     const size_t chunks = cb.size() - 1;
-    const uint8_t* in_alias = ctx->zero_copy_in ? device_alias(in) : nullptr;  // pinned input: read in place
+    const bool predict = ctx->pred_row_bytes != 0;
+    // pinned input is read in place, unless the predictor has to rewrite it on the device first
+    const uint8_t* in_alias = (ctx->zero_copy_in && !predict) ? device_alias(in) : nullptr;
     uint64_t hbase = 0;  // dense bytes placed so far
     bool overflow = false;
 
@@ -518,6 +539,11 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         d.detail = (uint32_t*)hs.detail.p;
         d.code_size = code_size ? (const uint8_t*)hs.cs.p : nullptr;
         d.n = m;
+        if (predict) {
+            CK(predictor_launch(0, (uint8_t*)hs.in.p - in_lo, d.in_off, nullptr, m, ctx->pred_row_bytes,
+                                ctx->pred_spp, ctx->num_sms, s), "predictor launch");
+            ctx->launches += 1;
+        }
         int rc = run_device(ctx, params, &d, s, Op::Encode);
         if (rc != SLZW_RC_OK) return rc;
         CK(compact_launch(d.out, d.out_off, d.out_len, m, align, (uint8_t*)hs.dense.p,
@@ -737,6 +763,44 @@ int slzw_compact_device(slzw_ctx* ctx, const uint8_t* src, const uint64_t* src_o
     CK(compact_launch(src, src_off, len, n, align, dst, dst_off, ctx->num_sms,
                       (cudaStream_t)cuda_stream), "compaction launch");
     ctx->launches += 2;
+    return SLZW_RC_OK;
+}
+
+static bool predictor_args_ok(uint32_t row_bytes, uint32_t spp) {
+    return row_bytes > 0 && spp >= 1 && spp <= 4 && row_bytes % spp == 0;
+}
+
+int slzw_tiff_predictor_device(slzw_ctx* ctx, int direction, uint8_t* data, const uint64_t* off,
+                               const uint64_t* len, uint64_t n, uint32_t row_bytes,
+                               uint32_t samples_per_pixel, void* cuda_stream) {
+    if (!ctx) return SLZW_RC_INVALID;
+    if ((direction != SLZW_PREDICTOR_DIFFERENCE && direction != SLZW_PREDICTOR_ACCUMULATE) ||
+        !predictor_args_ok(row_bytes, samples_per_pixel) || (n && (!data || !off))) {
+        snprintf(ctx->err, sizeof ctx->err,
+                 "invalid predictor arguments (8-bit samples, 1..4 per pixel, row_bytes a multiple)");
+        return SLZW_RC_INVALID;
+    }
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
+    CK(predictor_launch(direction, data, off, len, n, row_bytes, samples_per_pixel, ctx->num_sms,
+                        (cudaStream_t)cuda_stream), "predictor launch");
+    ctx->launches += n ? 1 : 0;
+    return SLZW_RC_OK;
+}
+
+int slzw_set_tiff_predictor(slzw_ctx* ctx, uint32_t row_bytes, uint32_t samples_per_pixel) {
+    if (!ctx) return SLZW_RC_INVALID;
+    if (row_bytes == 0 && samples_per_pixel == 0) {
+        ctx->pred_row_bytes = ctx->pred_spp = 0;
+        return SLZW_RC_OK;
+    }
+    if (!predictor_args_ok(row_bytes, samples_per_pixel)) {
+        snprintf(ctx->err, sizeof ctx->err,
+                 "invalid predictor arguments (8-bit samples, 1..4 per pixel, row_bytes a multiple)");
+        return SLZW_RC_INVALID;
+    }
+    ctx->pred_row_bytes = row_bytes;
+    ctx->pred_spp = samples_per_pixel;
     return SLZW_RC_OK;
 }
 
