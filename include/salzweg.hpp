@@ -18,14 +18,23 @@
 // `R: Read` becomes anything with data()/size() of bytes or a std::istream, `W: Write` a
 // std::ostream or a std::vector<uint8_t>; `Result<_, E>` becomes an exception of type E thrown
 // AFTER the bytes produced before the error have reached the writer, as in the reference.
-// New relative to the reference: encode_batch / decode_batch (many independent streams per call).
+// New relative to the reference: encode_batch / decode_batch (many independent streams per call) and
+// namespace coalesced -- the same types for multi-threaded callers, whose concurrent one-stream calls
+// are merged into batched launches.
 // There is no CPU path: the first call on a machine without an sm_100 GPU throws std::runtime_error.
 #ifndef SALZWEG_HPP
 #define SALZWEG_HPP
 
+#include <chrono>
+#include <condition_variable>
 #include <cstdint>
+#include <cstring>
+#include <exception>
 #include <istream>
 #include <iterator>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <ostream>
 #include <stdexcept>
 #include <string>
@@ -124,8 +133,8 @@ struct DecodingError : std::runtime_error {
 
 namespace detail {
 
-[[noreturn]] inline void launch_failure(const char* what) {
-    throw std::runtime_error(std::string(what) + ": " + slzw_last_error(context()));
+[[noreturn]] inline void launch_failure(const char* what, slzw_ctx* ctx = nullptr) {
+    throw std::runtime_error(std::string(what) + ": " + slzw_last_error(ctx ? ctx : context()));
 }
 
 inline void throw_encoding(uint32_t st, uint32_t det, uint8_t cs) {
@@ -173,144 +182,185 @@ void run_decode(const uint8_t* data, size_t n, W into, const slzw_params& p) {
     if (st != SLZW_OK) throw_decoding((uint32_t)st, det);
 }
 
-// The four codecs differ only in how their arguments map to slzw_params; ENC selects the direction.
 template <bool ENC, class W>
+void run_coalesced(const uint8_t* data, size_t n, W into, const slzw_params& p);
+
+// The four codecs differ only in how their arguments map to slzw_params; ENC selects the direction,
+// COALESCE whether the call is its own launch or joins the calls of other threads.
+template <bool ENC, bool COALESCE, class W>
 void run(const uint8_t* data, size_t n, W into, const slzw_params& p) {
-    if (ENC) run_encode(data, n, into, p);
+    if constexpr (COALESCE) run_coalesced<ENC>(data, n, into, p);
+    else if constexpr (ENC) run_encode(data, n, into, p);
     else run_decode(data, n, into, p);
 }
 
 // Argument adapters shared by every type: (bytes | istream) x (ostream | vector) and *_to_vec.
-template <bool ENC, class Data, class Into>
+template <bool ENC, bool COALESCE, class Data, class Into>
 void dispatch(Data& data, Into& into, const slzw_params& p) {
     using D = std::remove_cv_t<std::remove_reference_t<Data>>;
     using I = std::remove_cv_t<std::remove_reference_t<Into>>;
     if constexpr (std::is_base_of_v<std::istream, D>) {
         const std::vector<uint8_t> bytes = read_all(data);
-        dispatch<ENC>(bytes, into, p);
+        dispatch<ENC, COALESCE>(bytes, into, p);
     } else if constexpr (std::is_base_of_v<std::ostream, I>) {
-        run<ENC>(reinterpret_cast<const uint8_t*>(data.data()), data.size(), StreamWriter{into}, p);
+        run<ENC, COALESCE>(reinterpret_cast<const uint8_t*>(data.data()), data.size(), StreamWriter{into}, p);
     } else {
         static_assert(std::is_same_v<I, std::vector<uint8_t>>, "into: std::ostream or std::vector<uint8_t>");
-        run<ENC>(reinterpret_cast<const uint8_t*>(data.data()), data.size(), VecWriter{into}, p);
+        run<ENC, COALESCE>(reinterpret_cast<const uint8_t*>(data.data()), data.size(), VecWriter{into}, p);
     }
 }
-template <bool ENC, class Data>
+template <bool ENC, bool COALESCE, class Data>
 std::vector<uint8_t> to_vec(Data& data, const slzw_params& p) {
     std::vector<uint8_t> v;
-    dispatch<ENC>(data, v, p);  // like the reference, the partially filled Vec is dropped with the error
+    dispatch<ENC, COALESCE>(data, v, p);  // like the reference, the partially filled Vec is dropped with the error
     return v;
 }
 
 }  // namespace detail
 
 // ---- encoders --------------------------------------------------------------------------------------
-struct VariableEncoder {
+template <bool COALESCE>
+struct BasicVariableEncoder {
     template <class R, class W>
     static void encode(R&& data, W&& into, uint8_t code_size, Endianness endianness, CodeSizeStrategy strategy) {
-        detail::dispatch<true>(data, into, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
+        detail::dispatch<true, COALESCE>(data, into, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
     }
     template <class R>
     static std::vector<uint8_t> encode_to_vec(R&& data, uint8_t code_size, Endianness endianness,
                                               CodeSizeStrategy strategy) {
-        return detail::to_vec<true>(data, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
+        return detail::to_vec<true, COALESCE>(data, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
     }
 };
 
-struct GifStyleEncoder {
+template <bool COALESCE>
+struct BasicGifStyleEncoder {
     template <class R, class W>
     static void encode(R&& data, W&& into, uint8_t code_size) {
-        VariableEncoder::encode(data, into, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
+        BasicVariableEncoder<COALESCE>::encode(data, into, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
     }
     template <class R>
     static std::vector<uint8_t> encode_to_vec(R&& data, uint8_t code_size) {
-        return VariableEncoder::encode_to_vec(data, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
+        return BasicVariableEncoder<COALESCE>::encode_to_vec(data, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
     }
 };
 
-struct TiffStyleEncoder {
+template <bool COALESCE>
+struct BasicTiffStyleEncoder {
     template <class R, class W>
     static void encode(R&& data, W&& into) {
-        VariableEncoder::encode(data, into, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
+        BasicVariableEncoder<COALESCE>::encode(data, into, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
     }
     template <class R>
     static std::vector<uint8_t> encode_to_vec(R&& data) {
-        return VariableEncoder::encode_to_vec(data, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
+        return BasicVariableEncoder<COALESCE>::encode_to_vec(data, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
     }
 };
 
-struct FixedEncoder {
+template <bool COALESCE>
+struct BasicFixedEncoder {
     template <class R, class W>
     static void encode(R&& data, W&& into, Endianness endianness) {
-        detail::dispatch<true>(data, into, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
+        detail::dispatch<true, COALESCE>(data, into, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
     }
     template <class R>
     static std::vector<uint8_t> encode_to_vec(R&& data, Endianness endianness) {
-        return detail::to_vec<true>(data, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
+        return detail::to_vec<true, COALESCE>(data, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
     }
 };
 
 // ---- decoders --------------------------------------------------------------------------------------
-struct VariableDecoder {
+template <bool COALESCE>
+struct BasicVariableDecoder {
     template <class R, class W>
     static void decode(R&& data, W&& into, uint8_t code_size, Endianness endianness, CodeSizeStrategy strategy) {
-        detail::dispatch<false>(data, into, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
+        detail::dispatch<false, COALESCE>(data, into, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
     }
     template <class R>
     static std::vector<uint8_t> decode_to_vec(R&& data, uint8_t code_size, Endianness endianness,
                                               CodeSizeStrategy strategy) {
-        return detail::to_vec<false>(data, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
+        return detail::to_vec<false, COALESCE>(data, detail::params(SLZW_FLAVOUR_VARIABLE, code_size, endianness, strategy));
     }
 };
 
-struct GifStyleDecoder {
+template <bool COALESCE>
+struct BasicGifStyleDecoder {
     template <class R, class W>
     static void decode(R&& data, W&& into, uint8_t code_size) {
-        VariableDecoder::decode(data, into, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
+        BasicVariableDecoder<COALESCE>::decode(data, into, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
     }
     template <class R>
     static std::vector<uint8_t> decode_to_vec(R&& data, uint8_t code_size) {
-        return VariableDecoder::decode_to_vec(data, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
+        return BasicVariableDecoder<COALESCE>::decode_to_vec(data, code_size, Endianness::LittleEndian, CodeSizeStrategy::Default);
     }
 };
 
-struct TiffStyleDecoder {
+template <bool COALESCE>
+struct BasicTiffStyleDecoder {
     template <class R, class W>
     static void decode(R&& data, W&& into) {
-        VariableDecoder::decode(data, into, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
+        BasicVariableDecoder<COALESCE>::decode(data, into, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
     }
     template <class R>
     static std::vector<uint8_t> decode_to_vec(R&& data) {
-        return VariableDecoder::decode_to_vec(data, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
+        return BasicVariableDecoder<COALESCE>::decode_to_vec(data, 8, Endianness::BigEndian, CodeSizeStrategy::Tiff);
     }
 };
 
-struct FixedDecoder {
+template <bool COALESCE>
+struct BasicFixedDecoder {
     template <class R, class W>
     static void decode(R&& data, W&& into, Endianness endianness) {
-        detail::dispatch<false>(data, into, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
+        detail::dispatch<false, COALESCE>(data, into, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
     }
     template <class R>
     static std::vector<uint8_t> decode_to_vec(R&& data, Endianness endianness) {
-        return detail::to_vec<false>(data, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
+        return detail::to_vec<false, COALESCE>(data, detail::params(SLZW_FLAVOUR_FIXED, 0, endianness, CodeSizeStrategy::Default));
     }
 };
 
 /// Extension (not in the reference): VariableDecoder that tolerates deferred clear codes -- a full
 /// dictionary freezes until the next clear code instead of raising MissingClearCode
 /// (SLZW_FLAVOUR_VARIABLE_LENIENT in slzw.h).
-struct LenientDecoder {
+template <bool COALESCE>
+struct BasicLenientDecoder {
     template <class R, class W>
     static void decode(R&& data, W&& into, uint8_t code_size, Endianness endianness, CodeSizeStrategy strategy) {
-        detail::dispatch<false>(data, into,
+        detail::dispatch<false, COALESCE>(data, into,
                                 detail::params(SLZW_FLAVOUR_VARIABLE_LENIENT, code_size, endianness, strategy));
     }
     template <class R>
     static std::vector<uint8_t> decode_to_vec(R&& data, uint8_t code_size, Endianness endianness,
                                               CodeSizeStrategy strategy) {
-        return detail::to_vec<false>(data, detail::params(SLZW_FLAVOUR_VARIABLE_LENIENT, code_size, endianness, strategy));
+        return detail::to_vec<false, COALESCE>(data, detail::params(SLZW_FLAVOUR_VARIABLE_LENIENT, code_size, endianness, strategy));
     }
 };
+
+// The reference's names: every call is its own launch (a batch of one).
+using VariableEncoder = BasicVariableEncoder<false>;
+using GifStyleEncoder = BasicGifStyleEncoder<false>;
+using TiffStyleEncoder = BasicTiffStyleEncoder<false>;
+using FixedEncoder = BasicFixedEncoder<false>;
+using VariableDecoder = BasicVariableDecoder<false>;
+using GifStyleDecoder = BasicGifStyleDecoder<false>;
+using TiffStyleDecoder = BasicTiffStyleDecoder<false>;
+using FixedDecoder = BasicFixedDecoder<false>;
+using LenientDecoder = BasicLenientDecoder<false>;
+
+/// Streaming facade.  The same types and signatures, for callers that keep the
+/// reference's one-stream-per-call shape but call from many threads (a rayon-style parallel loop
+/// over strips or frames): concurrent calls with the same flavour / bit order are coalesced into
+/// one batched launch (group commit), each caller gets its own stream's bytes and error back.
+namespace coalesced {
+using VariableEncoder = BasicVariableEncoder<true>;
+using GifStyleEncoder = BasicGifStyleEncoder<true>;
+using TiffStyleEncoder = BasicTiffStyleEncoder<true>;
+using FixedEncoder = BasicFixedEncoder<true>;
+using VariableDecoder = BasicVariableDecoder<true>;
+using GifStyleDecoder = BasicGifStyleDecoder<true>;
+using TiffStyleDecoder = BasicTiffStyleDecoder<true>;
+using FixedDecoder = BasicFixedDecoder<true>;
+using LenientDecoder = BasicLenientDecoder<true>;
+}  // namespace coalesced
 
 // ---- batches (new relative to the reference) --------------------------------------------------------
 /// One stream's outcome of a batched call: the bytes produced (also those before an error) and the
@@ -321,30 +371,66 @@ struct StreamResult {
     bool ok() const { return status == SLZW_OK; }
 };
 
+namespace detail {
+
+inline std::vector<StreamResult> collect(const std::vector<uint8_t>& out, const std::vector<uint64_t>& out_off,
+                                         const std::vector<uint64_t>& len, const std::vector<uint32_t>& st,
+                                         const std::vector<uint32_t>& det) {
+    std::vector<StreamResult> res(len.size());
+    for (size_t i = 0; i < res.size(); i++) {
+        res[i].bytes.assign(out.begin() + out_off[i], out.begin() + out_off[i] + len[i]);
+        res[i].status = st[i];
+        res[i].detail = det[i];
+    }
+    return res;
+}
+
+inline std::vector<StreamResult> encode_batch(slzw_ctx* ctx, const slzw_params& p, const uint8_t* data,
+                                              const std::vector<uint64_t>& offsets, const uint8_t* code_sizes) {
+    const uint64_t n = offsets.empty() ? 0 : offsets.size() - 1;
+    if (n == 0) return {};
+    std::vector<uint64_t> out_off(n + 1, 0), len(n);
+    for (uint64_t i = 0; i < n; i++)
+        out_off[i + 1] = out_off[i] + ((slzw_encode_bound(&p, offsets[i + 1] - offsets[i]) + 15) & ~15ull);
+    std::vector<uint8_t> out(out_off[n] ? out_off[n] : 1);
+    std::vector<uint32_t> st(n), det(n);
+    slzw_batch b{data, offsets.data(), out.data(), out_off.data(), len.data(), st.data(), det.data(), code_sizes, n};
+    if (slzw_encode_batch_host(ctx, &p, &b) != SLZW_RC_OK) launch_failure("slzw_encode_batch_host", ctx);
+    return collect(out, out_off, len, st, det);
+}
+
+// capacities == nullptr: a size-only pass first, as decode_to_vec has no caller-supplied capacity
+inline std::vector<StreamResult> decode_batch(slzw_ctx* ctx, const slzw_params& p, const uint8_t* data,
+                                              const std::vector<uint64_t>& offsets, const uint64_t* capacities,
+                                              const uint8_t* code_sizes) {
+    const uint64_t n = offsets.empty() ? 0 : offsets.size() - 1;
+    if (n == 0) return {};
+    std::vector<uint64_t> out_off(n + 1, 0), len(n);
+    std::vector<uint32_t> st(n), det(n);
+    slzw_batch b{data, offsets.data(), nullptr, nullptr, len.data(), st.data(), det.data(), code_sizes, n};
+    if (!capacities) {
+        if (slzw_decoded_sizes_batch_host(ctx, &p, &b) != SLZW_RC_OK)
+            launch_failure("slzw_decoded_sizes_batch_host", ctx);
+        capacities = len.data();
+    }
+    for (uint64_t i = 0; i < n; i++) out_off[i + 1] = out_off[i] + capacities[i];
+    std::vector<uint8_t> out(out_off[n] ? out_off[n] : 1);
+    b.out = out.data();
+    b.out_off = out_off.data();
+    if (slzw_decode_batch_host(ctx, &p, &b) != SLZW_RC_OK) launch_failure("slzw_decode_batch_host", ctx);
+    return collect(out, out_off, len, st, det);
+}
+
+}  // namespace detail
+
 /// Encodes streams data[offsets[i] .. offsets[i+1]) with one configuration; per-stream code sizes
 /// (GIF frames with different palettes) may be given in `code_sizes`.
 inline std::vector<StreamResult> encode_batch(const uint8_t* data, const std::vector<uint64_t>& offsets,
                                               uint8_t flavour, uint8_t code_size, Endianness endianness,
                                               CodeSizeStrategy strategy,
                                               const std::vector<uint8_t>* code_sizes = nullptr) {
-    const slzw_params p = detail::params(flavour, code_size, endianness, strategy);
-    const uint64_t n = offsets.empty() ? 0 : offsets.size() - 1;
-    std::vector<StreamResult> res(n);
-    if (n == 0) return res;
-    std::vector<uint64_t> out_off(n + 1, 0), len(n);
-    for (uint64_t i = 0; i < n; i++)
-        out_off[i + 1] = out_off[i] + ((slzw_encode_bound(&p, offsets[i + 1] - offsets[i]) + 15) & ~15ull);
-    std::vector<uint8_t> out(out_off[n] ? out_off[n] : 1);
-    std::vector<uint32_t> st(n), det(n);
-    slzw_batch b{data, offsets.data(), out.data(), out_off.data(), len.data(), st.data(), det.data(),
-                 code_sizes ? code_sizes->data() : nullptr, n};
-    if (slzw_encode_batch_host(detail::context(), &p, &b) != SLZW_RC_OK) detail::launch_failure("slzw_encode_batch_host");
-    for (uint64_t i = 0; i < n; i++) {
-        res[i].bytes.assign(out.begin() + out_off[i], out.begin() + out_off[i] + len[i]);
-        res[i].status = st[i];
-        res[i].detail = det[i];
-    }
-    return res;
+    return detail::encode_batch(detail::context(), detail::params(flavour, code_size, endianness, strategy), data, offsets,
+                                code_sizes ? code_sizes->data() : nullptr);
 }
 
 /// Decodes streams data[offsets[i] .. offsets[i+1]); capacities[i] is the room given to stream i
@@ -353,24 +439,193 @@ inline std::vector<StreamResult> decode_batch(const uint8_t* data, const std::ve
                                               const std::vector<uint64_t>& capacities, uint8_t flavour,
                                               uint8_t code_size, Endianness endianness, CodeSizeStrategy strategy,
                                               const std::vector<uint8_t>* code_sizes = nullptr) {
-    const slzw_params p = detail::params(flavour, code_size, endianness, strategy);
-    const uint64_t n = offsets.empty() ? 0 : offsets.size() - 1;
-    std::vector<StreamResult> res(n);
-    if (n == 0) return res;
-    std::vector<uint64_t> out_off(n + 1, 0), len(n);
-    for (uint64_t i = 0; i < n; i++) out_off[i + 1] = out_off[i] + capacities[i];
-    std::vector<uint8_t> out(out_off[n] ? out_off[n] : 1);
-    std::vector<uint32_t> st(n), det(n);
-    slzw_batch b{data, offsets.data(), out.data(), out_off.data(), len.data(), st.data(), det.data(),
-                 code_sizes ? code_sizes->data() : nullptr, n};
-    if (slzw_decode_batch_host(detail::context(), &p, &b) != SLZW_RC_OK) detail::launch_failure("slzw_decode_batch_host");
-    for (uint64_t i = 0; i < n; i++) {
-        res[i].bytes.assign(out.begin() + out_off[i], out.begin() + out_off[i] + len[i]);
-        res[i].status = st[i];
-        res[i].detail = det[i];
-    }
-    return res;
+    return detail::decode_batch(detail::context(), detail::params(flavour, code_size, endianness, strategy), data, offsets,
+                                capacities.data(), code_sizes ? code_sizes->data() : nullptr);
 }
+
+// ---- coalescing of one-stream calls -------------------------------------------------
+namespace coalesced {
+
+/// How long the thread that runs a batch waits for other callers to join it, and when it stops
+/// waiting early.  Process-wide; the defaults suit a parallel loop over strips or frames.
+struct Options {
+    std::chrono::microseconds linger{200};
+    size_t max_streams = 65536;
+    size_t max_bytes = size_t(256) << 20;
+};
+struct Stats {
+    uint64_t streams = 0, batches = 0, largest_batch = 0;
+};
+
+}  // namespace coalesced
+
+namespace detail {
+
+// Group commit: a caller queues its stream; if nobody is running a batch it becomes the leader,
+// lingers a moment, takes everything queued (its own stream included), runs ONE batched call on its
+// the coalescer's own context and hands the results out.  Streams that arrive while a batch runs wait for
+// the next leader.  One instance per (direction, flavour, bit order, width strategy): the code
+// size travels per stream.
+class Coalescer {
+  public:
+    Coalescer(bool encoder, slzw_params p) : encoder_(encoder), params_(p) {}
+    ~Coalescer() { slzw_destroy(ctx_); }
+    Coalescer(const Coalescer&) = delete;
+    Coalescer& operator=(const Coalescer&) = delete;
+
+    StreamResult run(const uint8_t* data, size_t n, uint8_t code_size) {
+        Request r;
+        r.data = data, r.n = n, r.code_size = code_size;
+        std::unique_lock<std::mutex> lk(mu_);
+        queue_.push_back(&r);
+        queued_bytes_ += n;
+        if (leader_ && (queue_.size() >= options_.max_streams || queued_bytes_ >= options_.max_bytes)) cv_.notify_all();
+        while (!r.done) {
+            if (leader_) {
+                cv_.wait(lk);
+                continue;
+            }
+            leader_ = true;
+            const auto deadline = std::chrono::steady_clock::now() + options_.linger;
+            while (queue_.size() < options_.max_streams && queued_bytes_ < options_.max_bytes &&
+                   cv_.wait_until(lk, deadline) != std::cv_status::timeout) {
+            }
+            std::vector<Request*> batch;
+            batch.swap(queue_);
+            queued_bytes_ = 0;
+            lk.unlock();
+            std::exception_ptr failure;
+            try {
+                execute(batch);
+            } catch (...) {
+                failure = std::current_exception();  // a failed launch fails every stream of the batch
+            }
+            lk.lock();
+            for (Request* q : batch) {
+                q->failure = failure;
+                q->done = true;
+            }
+            stats_.streams += batch.size();
+            stats_.batches += 1;
+            if (batch.size() > stats_.largest_batch) stats_.largest_batch = batch.size();
+            leader_ = false;
+            cv_.notify_all();
+        }
+        lk.unlock();
+        if (r.failure) std::rethrow_exception(r.failure);
+        return std::move(r.result);
+    }
+
+    void set_options(const coalesced::Options& o) {
+        std::lock_guard<std::mutex> lk(mu_);
+        options_ = o;
+    }
+    coalesced::Stats stats() {
+        std::lock_guard<std::mutex> lk(mu_);
+        return stats_;
+    }
+
+  private:
+    struct Request {
+        const uint8_t* data = nullptr;
+        size_t n = 0;
+        uint8_t code_size = 0;
+        bool done = false;
+        StreamResult result;
+        std::exception_ptr failure;
+    };
+
+    // only ever entered by the current leader
+    void execute(const std::vector<Request*>& batch) {
+        if (!ctx_) {
+            const int rc = slzw_create(0, &ctx_);
+            if (rc != SLZW_RC_OK)
+                throw std::runtime_error(rc == SLZW_RC_NO_DEVICE
+                                             ? "salzweg (B200): no usable sm_100 CUDA device, and there is no CPU path"
+                                             : "salzweg (B200): slzw_create failed");
+        }
+        std::vector<uint64_t> offsets(batch.size() + 1, 0);
+        for (size_t i = 0; i < batch.size(); i++) offsets[i + 1] = offsets[i] + batch[i]->n;
+        std::vector<uint8_t> data(offsets.back() ? offsets.back() : 1), code_sizes(batch.size());
+        for (size_t i = 0; i < batch.size(); i++) {
+            if (batch[i]->n) std::memcpy(data.data() + offsets[i], batch[i]->data, batch[i]->n);
+            code_sizes[i] = batch[i]->code_size;
+        }
+        std::vector<StreamResult> res =
+            encoder_ ? encode_batch(ctx_, params_, data.data(), offsets, code_sizes.data())
+                     : decode_batch(ctx_, params_, data.data(), offsets, nullptr, code_sizes.data());
+        for (size_t i = 0; i < batch.size(); i++) batch[i]->result = std::move(res[i]);
+    }
+
+    const bool encoder_;
+    const slzw_params params_;
+    slzw_ctx* ctx_ = nullptr;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::vector<Request*> queue_;
+    size_t queued_bytes_ = 0;
+    bool leader_ = false;
+    coalesced::Options options_;
+    coalesced::Stats stats_;
+};
+
+struct CoalescerRegistry {
+    std::mutex mu;
+    std::map<uint32_t, std::unique_ptr<Coalescer>> by_key;
+    coalesced::Options options;
+    static CoalescerRegistry& instance() {
+        static CoalescerRegistry r;
+        return r;
+    }
+    Coalescer& get(bool encoder, const slzw_params& p) {
+        const uint32_t key = (encoder ? 1u : 0u) | (uint32_t)p.flavour << 8 | (uint32_t)p.big_endian << 16 |
+                             (uint32_t)p.tiff_early_change << 24;
+        std::lock_guard<std::mutex> lk(mu);
+        std::unique_ptr<Coalescer>& c = by_key[key];
+        if (!c) {
+            c.reset(new Coalescer(encoder, p));
+            c->set_options(options);
+        }
+        return *c;
+    }
+};
+
+template <bool ENC, class W>
+void run_coalesced(const uint8_t* data, size_t n, W into, const slzw_params& p) {
+    StreamResult r = CoalescerRegistry::instance().get(ENC, p).run(data, n, p.code_size);
+    into.write_all(r.bytes.data(), r.bytes.size());  // bytes produced before an error stay written
+    if (!r.ok()) {
+        if (ENC) throw_encoding(r.status, r.detail, p.code_size);
+        else throw_decoding(r.status, r.detail);
+    }
+}
+
+}  // namespace detail
+
+namespace coalesced {
+
+inline void set_options(const Options& o) {
+    detail::CoalescerRegistry& r = detail::CoalescerRegistry::instance();
+    std::lock_guard<std::mutex> lk(r.mu);
+    r.options = o;
+    for (auto& kv : r.by_key) kv.second->set_options(o);
+}
+
+/// Totals over every coalescer of the process (streams / batches = average batch size).
+inline Stats stats() {
+    detail::CoalescerRegistry& r = detail::CoalescerRegistry::instance();
+    std::lock_guard<std::mutex> lk(r.mu);
+    Stats t;
+    for (auto& kv : r.by_key) {
+        const Stats s = kv.second->stats();
+        t.streams += s.streams;
+        t.batches += s.batches;
+        if (s.largest_batch > t.largest_batch) t.largest_batch = s.largest_batch;
+    }
+    return t;
+}
+
+}  // namespace coalesced
 
 }  // namespace salzweg
 

@@ -185,6 +185,9 @@ SLZW_API uint64_t slzw_encode_bound(const slzw_params* params, uint64_t n);
  * (decoder.rs:163-172), which has no caller-supplied capacity. */
 SLZW_API int slzw_decoded_sizes_batch_device(slzw_ctx* ctx, const slzw_params* params,
                                     const slzw_batch* batch, void* cuda_stream);
+/* The same for a host-resident batch (batch->out/out_off may be NULL). */
+SLZW_API int slzw_decoded_sizes_batch_host(slzw_ctx* ctx, const slzw_params* params,
+                                  const slzw_batch* batch);
 
 /* ---- compaction (scheduler output stage) -------------------------------------------------
  * dst_off[0..n] = exclusive prefix sum of len[0..n), each length rounded up to a multiple of

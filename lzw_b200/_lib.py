@@ -86,6 +86,7 @@ SYMBOLS = {
     "slzw_decoded_sizes_batch_device": (C.c_int, [C.c_void_p, _P(Params), _P(Batch), C.c_void_p]),
     "slzw_compact_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                       C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "slzw_decoded_sizes_batch_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "slzw_tiff_predictor_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p]),
     "slzw_set_tiff_predictor": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),

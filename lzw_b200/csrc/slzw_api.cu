@@ -721,6 +721,10 @@ int slzw_decode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_
     return run_host(ctx, params, batch, Op::Decode);
 }
 
+int slzw_decoded_sizes_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch) {
+    return run_host(ctx, params, batch, Op::DecodedSizes);
+}
+
 int slzw_encode_batch_host_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
                                  const uint64_t* in_off, uint64_t n, const uint8_t* code_size,
                                  uint64_t align, uint8_t* out_dense, uint64_t out_cap,
