@@ -47,6 +47,11 @@ extern "C" {
                                 cuda_stream: *mut c_void) -> c_int;
     fn slzw_decode_batch_device(ctx: *mut SlzwCtx, p: *const SlzwParams, b: *const SlzwBatch,
                                 cuda_stream: *mut c_void) -> c_int;
+    #[allow(dead_code)]
+    fn slzw_decoded_sizes_batch_host(ctx: *mut SlzwCtx, p: *const SlzwParams, b: *const SlzwBatch) -> c_int;
+    /// TIFF Predictor = 2 inside the host batch calls (0, 0 = off)
+    #[allow(dead_code)]
+    fn slzw_set_tiff_predictor(ctx: *mut SlzwCtx, row_bytes: u32, samples_per_pixel: u32) -> c_int;
 }
 
 /// lzw/src/lib.rs:59-65
