@@ -345,6 +345,14 @@ struct ChunkStage {
     }
 };
 
+// An error in the middle of a pipelined call: copies of earlier chunks into the caller's buffers may
+// still be in flight, so the slots are drained before the call returns (the error text is kept).
+int drain_pipe(slzw_ctx* ctx, int rc) {
+    for (int i = 0; i < kPipe; i++) cudaStreamSynchronize(ctx->pipe[i].stream);
+    cudaGetLastError();
+    return rc;
+}
+
 // Host path: the batch goes through the device in chunks of streams, pipelined over kPipe
 // slots (H2D of chunk k+1, kernels of chunk k and D2H of chunk k-1 overlap), results land in the
 // caller's buffers.  Pinned host buffers (slzw_host_alloc) make the large copies asynchronous.
@@ -452,12 +460,12 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
 
     int rc;
     for (size_t k = 0; k < chunks; k++) {
-        if ((rc = enqueue(k)) != SLZW_RC_OK) return rc;
+        if ((rc = enqueue(k)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
         // the slot chunk k+1 will use is the one of chunk k+1-kPipe: finish that chunk now
-        if (k + 1 >= (size_t)kPipe && (rc = finalize(k + 1 - kPipe)) != SLZW_RC_OK) return rc;
+        if (k + 1 >= (size_t)kPipe && (rc = finalize(k + 1 - kPipe)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
     }
     for (size_t k = chunks >= (size_t)kPipe ? chunks - kPipe + 1 : 0; k < chunks; k++)
-        if ((rc = finalize(k)) != SLZW_RC_OK) return rc;
+        if ((rc = finalize(k)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
     return SLZW_RC_OK;
 }
 
@@ -577,13 +585,13 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
 
     int rc;
     for (size_t k = 0; k < chunks; k++) {
-        if ((rc = enqueue(k)) != SLZW_RC_OK) return rc;
+        if ((rc = enqueue(k)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
         // chunks are placed in order, one chunk behind the newest launch; the slot chunk k+1 will
         // use (that of chunk k+1-kPipe) has been placed by then and its copy is ordered before
         // the reuse by the slot's stream
-        if (k >= 1 && (rc = place(k - 1)) != SLZW_RC_OK) return rc;
+        if (k >= 1 && (rc = place(k - 1)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
     }
-    if ((rc = place(chunks - 1)) != SLZW_RC_OK) return rc;
+    if ((rc = place(chunks - 1)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
     for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->pipe[i].stream), "cudaStreamSynchronize");
     if (needed) *needed = hbase;
     if (overflow) {
