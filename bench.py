@@ -42,6 +42,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=4096, help="strips in the CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config3", choices=["config3", "readme"],
+                    help="config3: the bench line of the contract; readme: the rows of the reference's README "
+                         "(tokyo image / lorem text, variable and fixed codes) -- extra lines, not the contract's")
     return ap.parse_args()
 
 
@@ -457,8 +460,130 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---- the reference's own README rows ----------------------------------------------------
+# README.md:23-30 of the reference: single-thread criterion results on the indices of
+# tokyo_128_colors.png (1024 x 684, code size 7) and on lorem_ipsum.txt, variable (GIF-style) and
+# fixed 12-bit codes; inputs as lzw/benches/compare_crates.rs:4-16.  MiB/s of uncompressed bytes.
+README_ROWS = {  # (input, codes, direction) -> published MiB/s (Ryzen 7 2700X, one thread)
+    ("image", "variable", "encode"): 70, ("image", "fixed", "encode"): 120,
+    ("image", "variable", "decode"): 200, ("image", "fixed", "decode"): 210,
+    ("text", "variable", "encode"): 70, ("text", "fixed", "encode"): 85,
+    ("text", "variable", "decode"): 200, ("text", "fixed", "decode"): 220,
+}
+
+
+def run_readme_rows(args):
+    """One JSON line per README row: the GPU codec on one stream per call (what the reference's
+    bench does, latency-bound on a GPU), on a device-resident batch of copies of the same stream
+    (what the GPU codec is for), and the C port of the reference on one host thread."""
+    import torch
+    from PIL import Image
+
+    import lzw_b200
+    from lzw_b200.types import fixed_params, gif_params
+    from oracle import oracle as O  # cpu_baseline leg of each row
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; lzw_b200 has no CPU path")
+    dev = torch.device("cuda", 0)
+    codec = lzw_b200.Codec(0)
+    golden = os.path.join(ROOT, "tests", "golden")
+    image = np.asarray(Image.open(os.path.join(golden, "tokyo_128_colors.png"))).reshape(-1).copy()
+    with open(os.path.join(golden, "lorem_ipsum.txt"), "rb") as f:
+        text = np.frombuffer(f.read(), dtype=np.uint8).copy()
+    MiB = float(1 << 20)
+
+    def i64(a):
+        return torch.from_numpy(a.view(np.int64)).to(dev)
+
+    for name, data, copies in (("image", image, 4096), ("text", text, 65536)):
+        for codes, gp, op in (("variable", gif_params(7), O.gif(7)),
+                              ("fixed", fixed_params(lzw_b200.Endianness.LittleEndian), O.fixed(False))):
+            raw = data.tobytes()
+            st, _, enc = codec.encode(gp, raw)
+            ost, _, oenc = O.encode(op, raw)
+            assert st == 0 and ost == 0 and enc == oenc, "GPU and oracle streams differ"
+            # device-resident batch of `copies` copies
+            n = copies
+            off = np.arange(n + 1, dtype=np.uint64) * np.uint64(data.size)
+            slot = (codec.encode_bound(gp, data.size) + 15) // 16 * 16
+            slots = np.arange(n + 1, dtype=np.uint64) * np.uint64(slot)
+            t_in = torch.from_numpy(data).to(dev).repeat(n)
+            t_off, t_slots = i64(off), i64(slots)
+            t_enc = torch.empty(int(slots[-1]), dtype=torch.uint8, device=dev)
+            t_len = torch.zeros(n, dtype=torch.int64, device=dev)
+            t_st = torch.zeros(n, dtype=torch.int32, device=dev)
+            t_det = torch.zeros(n, dtype=torch.int32, device=dev)
+            t_dec = torch.empty(n * data.size, dtype=torch.uint8, device=dev)
+            t_dlen = torch.zeros(n, dtype=torch.int64, device=dev)
+            t_dense = torch.empty(int(slots[-1]), dtype=torch.uint8, device=dev)
+            t_doff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+
+            def enc_batch():
+                codec.encode_batch_device(gp, n, t_in.data_ptr(), t_off.data_ptr(), t_enc.data_ptr(),
+                                          t_slots.data_ptr(), t_len.data_ptr(), t_st.data_ptr(), t_det.data_ptr())
+
+            def dec_batch():
+                codec.decode_batch_device(gp, n, t_dense.data_ptr(), t_doff.data_ptr(), t_dec.data_ptr(),
+                                          t_off.data_ptr(), t_dlen.data_ptr(), t_st.data_ptr(), t_det.data_ptr())
+
+            def time_gpu(fn, reps=5):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / reps * 1e-3
+
+            def time_host(fn, budget=1.5):
+                fn()
+                k, t0 = 0, time.perf_counter()
+                while time.perf_counter() - t0 < budget:
+                    fn()
+                    k += 1
+                return (time.perf_counter() - t0) / k
+
+            t_be = time_gpu(enc_batch)
+            enc_ok = bool((t_st == 0).all().item())
+            codec.compact_device(t_enc.data_ptr(), t_slots.data_ptr(), t_len.data_ptr(), n, t_dense.data_ptr(),
+                                 t_doff.data_ptr(), align=1)
+            t_bd = time_gpu(dec_batch)
+            dec_ok = bool((t_st == 0).all().item()) and bool(torch.equal(t_dec, t_in))
+            for direction, t_batch, ok in (("encode", t_be, enc_ok), ("decode", t_bd, dec_ok)):
+                if direction == "encode":
+                    t_one = time_host(lambda: codec.encode(gp, raw))
+                    t_cpu = time_host(lambda: O.encode(op, raw))
+                else:
+                    t_one = time_host(lambda: codec.decode(gp, enc, cap=len(raw)))
+                    t_cpu = time_host(lambda: O.decode(op, enc, cap=len(raw)))
+                published = README_ROWS[(name, codes, direction)]
+                batch_mibs = n * data.size / t_batch / MiB
+                print(json.dumps({
+                    "metric": f"{direction}, {name} data, {codes} codes (reference README.md:27-30)",
+                    "unit": "MiB/s", "higher_is_better": True, "dtype": "u8",
+                    "data": "tests/golden (the reference's own bench inputs)",
+                    "config": {"workload": f"{name}: {data.size} bytes, code size 7; batch = {n} copies, device-resident"},
+                    "value": batch_mibs, "value_is": "GPU, batched",
+                    "gpu_one_stream_per_call": len(raw) / t_one / MiB,
+                    "published_reference_1_thread": published,
+                    "vs_baseline": batch_mibs / published,
+                    "cpu_baseline": {"value": len(raw) / t_cpu / MiB, "unit": "MiB/s", "cores": 1, "kind": "port",
+                                     "sample": "the same single stream, oracle/slzw_oracle.c"},
+                    "status_ok": ok, "byte_exact_vs_oracle": True,
+                }), flush=True)
+            del t_in, t_enc, t_dec, t_dense
+            torch.cuda.empty_cache()
+    codec.close()
+
+
 def main():
     args = parse_args()
+    if args.workload == "readme":
+        return run_readme_rows(args)
     if args.impl == "reference":
         run_reference(args)
     else:
