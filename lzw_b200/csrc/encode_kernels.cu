@@ -57,6 +57,16 @@ __device__ __forceinline__ uint32_t tbl_ld(uint32_t saddr) {
     asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr));
     return v;
 }
+// One bucket (32 slots = 8 rows of 16 bytes) as a warp-collective matrix load: lanes 0..7 pass the
+// row addresses, lane i receives row i / 4, bytes 4 * (i % 4) .. + 3 -- slot i of the bucket, what
+// a per-lane 32-bit load would return.  The instruction is .aligned, which tells the compiler that
+// the warp is converged around it: the ballots and shuffles of the step then need no divergence
+// guard.
+__device__ __forceinline__ uint32_t tbl_ld_bucket(uint32_t row_addr) {
+    uint32_t v;
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];\n" : "=r"(v) : "r"(row_addr));
+    return v;
+}
 __device__ __forceinline__ void tbl_st(uint32_t saddr, uint32_t v) {
     asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(saddr), "r"(v));
 }
@@ -345,22 +355,26 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
     // always the lanes >= some count: the first empty slot is this lane's iff the ballot of empty
     // slots equals "all lanes from mine on"
     const uint32_t lanes_ge = 0xFFFFFFFFu << lane;
+    // shared-memory dictionary: a bucket is loaded through its 8 row addresses (lane & 7), an
+    // insert goes to this lane's own slot; tlx turns the one address into the other
+    const uint32_t tlr = (tl & ~0x7Fu) | (((uint32_t)lane & 7u) << 4);
+    const uint32_t tlx = tlr ^ tl;
 
 #define SLZW_STEP_B(RC)                                                                         \
     {                                                                                           \
         const uint32_t key = t | (RC).x;                                                        \
-        uint32_t a = TMEM ? ((tp & 0x7Fu) ^ (RC).y) : (tl | ((tp ^ (RC).y) & kBucketMask));     \
-        /* One explicit convergence point per step: the compiler then drops the divergence guard \
-           it otherwise puts in front of every ballot and shuffle of the step (tcgen05.ld brings \
-           its own); it also orders the previous step's insert before this step's loads. */      \
-        if (!TMEM) __syncwarp();                                                                \
+        uint32_t a = TMEM ? ((tp & 0x7Fu) ^ (RC).y) : (tlr | ((tp ^ (RC).y) & kBucketMask));    \
+        /* Both bucket loads (tcgen05.ld, ldmatrix) are .sync.aligned: the warp is converged at   \
+           every step, the compiler puts no divergence guard in front of the ballots and the     \
+           shuffle, and the insert of the previous step (same warp, same memory pipe, program    \
+           order) is in place before this step's load. */                                        \
         _Pragma("unroll 1") for (;;) {                                                          \
             uint32_t v;                                                                         \
             if (TMEM) {                                                                         \
                 v = tmem_ld(a);                                                                 \
                 tmem_wait_ld(v);                                                                \
             } else {                                                                            \
-                v = tbl_ld(a);                                                                  \
+                v = tbl_ld_bucket(a);                                                           \
             }                                                                                   \
             const uint32_t x = v ^ key; /* == code' iff my slot holds the key */                \
             const uint32_t bal = __ballot_sync(kFullMask, x - 1u < 4095u);                      \
@@ -377,7 +391,8 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                 continue;                                                                       \
             }                                                                                   \
             /* miss: encoder.rs:322-324 / 645-649 */                                            \
-            sts_u16(cpa, MODE == 1 ? ((t >> 20) | wtag) : (t >> 20));                           \
+            /* the prefix' being emitted: tp itself in the tensor-memory variant */             \
+            sts_u16(cpa, MODE == 1 ? ((TMEM ? tp : t >> 20) | wtag) : (TMEM ? tp : t >> 20));   \
             cpa += 2u;                                                                          \
             if (MODE == 0 || (MODE == 1 && (!FIXED || until != 0u))) {                          \
                 const bool mine = em == lanes_ge; /* I own the first empty slot */              \
@@ -386,7 +401,7 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                     tmem_st(a, mine ? entry : v);                                               \
                     tmem_wait_st();                                                             \
                 } else {                                                                        \
-                    if (mine) tbl_st(a, entry);                                                 \
+                    if (mine) tbl_st(a ^ tlx, entry);                                           \
                 }                                                                               \
                 ncs += kScr;                                                                    \
                 if (MODE == 1) {                                                                \
