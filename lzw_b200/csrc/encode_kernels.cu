@@ -685,11 +685,12 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
         if (len) {
             // inserts left before the next event against the most this tile can insert
             const int mode = (FIXED && m.until == 0u) ? 2 : (m.until > len ? 0 : 1);
-            // unroll of the common MODE 0 loop: 4 steps per iteration amortise the loop's own
-            // instructions (81.9 against 85.0 ms at config 3); 8 spill and run at 90.6 ms
+            // unroll of the MODE 0 and MODE 2 loops: 4 steps per iteration amortise the loop's own
+            // instructions (81.9 against 85.0 ms at config 3, 51.7 against 53.7 ms at config 5);
+            // 8 spill and run at 90.6 ms.  MODE 1 tiles are rare and keep U.
             constexpr int kU0 = SLZW_U0;
 #define SLZW_MATCH_B(TM, MD)                                                                        \
-    match_tile_bucket<FIXED, TM, (MD == 0 ? kU0 : U), MD>(table, TM ? 0u : (tb | (4u * (uint32_t)lane)), TM ? tb : 0u, rec, \
+    match_tile_bucket<FIXED, TM, (MD == 1 ? U : kU0), MD>(table, TM ? 0u : (tb | (4u * (uint32_t)lane)), TM ? tb : 0u, rec, \
                                         codes, lane, len, m, cs, inc, clear_code, first_code)
             if (TMEM) {
                 if (mode == 0) SLZW_MATCH_B(true, 0);
