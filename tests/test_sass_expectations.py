@@ -1,0 +1,64 @@
+"""What the design relies on in the generated code, checked on the built objects with cuobjdump
+(no GPU needed): the default encoder kernel keeps its dictionaries in tensor memory and shared
+memory (LDTM / STTM / LDSM), nothing spills to local memory in the codec kernels, and the
+shared-memory lookup step carries no divergence guard (profiles/r01_encode_notes.md)."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from tests.conftest import ROOT
+
+CSRC = os.path.join(ROOT, "lzw_b200", "csrc")
+
+
+def _functions(obj):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(os.path.join(CSRC, obj)) or not os.path.exists(exe):
+        pytest.skip("built objects or cuobjdump not available")
+    out = subprocess.run([exe, "-sass", os.path.join(CSRC, obj)], capture_output=True, text=True, check=True).stdout
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name and re.match(r"\s+/\*[0-9a-f]{4,}\*/", line):
+            funcs[name].append(line)
+    return funcs
+
+
+def _ops(lines):
+    ops = []
+    for line in lines:
+        body = re.sub(r"/\*.*?\*/", "", line).strip().rstrip(";").strip()
+        toks = [t for t in body.split() if not t.startswith("@")]
+        if toks:
+            ops.append(toks[0])
+    return ops
+
+
+def test_default_encoder_uses_tensor_memory_and_matrix_loads():
+    funcs = _functions("encode_kernels.o")
+    # slzw_encode_kernel<96, 12, 16, 2, true, FIXED>
+    default = {n: l for n, l in funcs.items() if "slzw_encode_kernelILi96ELi12ELi16ELi2ELb1E" in n}
+    assert len(default) == 2
+    for name, lines in default.items():
+        ops = _ops(lines)
+        assert any(o.startswith("LDTM") for o in ops), name          # tcgen05.ld
+        assert any(o.startswith("STTM") for o in ops), name          # tcgen05.st
+        assert any(o.startswith("LDSM") for o in ops), name          # ldmatrix bucket loads
+        assert not any(o.startswith(("LDL", "STL")) for o in ops), name  # no spills
+        # the instruction after an LDSM-based lookup reaches its ballot without a divergence guard
+        idx = [i for i, o in enumerate(ops) if o.startswith("LDSM")]
+        guarded = sum(1 for i in idx if any(o == "BRA.DIV" for o in ops[i:i + 12]))
+        assert guarded == 0, (name, guarded)
+
+
+def test_codec_kernels_do_not_spill():
+    for obj, key in (("decode_kernels.o", "slzw_decode_fast_kernelILi12ELi20E"), ("sched_kernels.o", "")):
+        for name, lines in _functions(obj).items():
+            if key in name:
+                assert not any(o.startswith(("LDL", "STL")) for o in _ops(lines)), name
