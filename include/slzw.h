@@ -141,6 +141,11 @@ SLZW_API uint32_t slzw_version(void);
  * copies up to `cap` stream ids into `ids` (may be NULL).  After a *_host call that was split
  * into several chunks it describes the last chunk only (ids relative to that chunk). */
 SLZW_API uint64_t slzw_last_deferred(slzw_ctx* ctx, uint32_t* ids, uint64_t cap);
+/* Diagnostics: input bytes of the most recent encode call of this context by the kind of warp
+ * that encoded them -- [0] one warp per stream, dictionary in tensor memory; [1] one warp per
+ * stream, dictionary in shared memory; [2] one lane per stream, shared memory; [3] one lane per
+ * stream, global memory (encode_kernels.cu).  Synchronises the device. */
+SLZW_API int slzw_last_encode_shares(slzw_ctx* ctx, uint64_t bytes[4]);
 
 /* ---- batched entry points (the hot path; new relative to the reference) ----------------- */
 /* Device-resident batch, asynchronous on `cuda_stream` (a cudaStream_t, may be NULL).

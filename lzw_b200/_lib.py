@@ -70,6 +70,7 @@ SYMBOLS = {
     "slzw_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "slzw_version": (C.c_uint32, []),
     "slzw_last_deferred": (C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "slzw_last_encode_shares": (C.c_int, [C.c_void_p, C.c_void_p]),
     "slzw_encode_batch_device": (C.c_int, [C.c_void_p, _P(Params), _P(Batch), C.c_void_p]),
     "slzw_decode_batch_device": (C.c_int, [C.c_void_p, _P(Params), _P(Batch), C.c_void_p]),
     "slzw_encode_batch_host": (C.c_int, [C.c_void_p, _P(Params), _P(Batch)]),

@@ -55,6 +55,13 @@ class Codec:
         n = int(self._lib.slzw_last_deferred(self._h, ids.ctypes.data, cap))
         return ids[: min(n, cap)] if n <= cap else np.concatenate([ids[:cap], np.full(n - cap, 0xFFFFFFFF, np.uint32)])
 
+    def last_encode_shares(self) -> np.ndarray:
+        """Input bytes of the last encode call by kind of warp (tensor-memory warp, shared-memory
+        warp, shared-memory lanes, global-memory lanes)."""
+        out = np.zeros(4, dtype=np.uint64)
+        self._check(self._lib.slzw_last_encode_shares(self._h, out.ctypes.data), "slzw_last_encode_shares")
+        return out
+
     def encode_bound(self, params: Params, n: int) -> int:
         return int(self._lib.slzw_encode_bound(C.byref(params), n))
 

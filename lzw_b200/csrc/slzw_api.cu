@@ -20,6 +20,7 @@ namespace slzw {
 void encode_select_config(int c);
 cudaError_t encode_configure();
 cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream);
+size_t encode_table_bytes(uint64_t n, int num_sms);
 // decode_kernels.cu
 size_t decode_exact_smem_bytes();
 int decode_exact_warps_per_cta();
@@ -77,12 +78,13 @@ struct Workspace {
     DevBuf order;  // n u32
     DevBuf retry;  // n u32: streams the fast decoder deferred
     DevBuf tables; // fast decoder: dictionaries of the warps that have none in shared memory
+    DevBuf enc_tables; // encoder: dictionaries of the lanes in global memory
     cudaEvent_t done = nullptr;
     bool used = false;
 };
 
 constexpr int kWorkspaces = 4;
-constexpr size_t kQueueWords = 4;
+constexpr size_t kQueueWords = 8;  // [4..7]: input bytes encoded per kind of warp (diagnostics)
 constexpr int kPipe = 3;
 // host-path chunks: at least this many input/output bytes each (a chunk must amortise the tail
 // of its longest stream), at most kMaxChunks per call
@@ -144,6 +146,7 @@ struct slzw_ctx {
     uint32_t pred_spp = 0;
     uint64_t launches = 0;
     int last_decode_ws = -1;  // workspace of the most recent decode call
+    int last_encode_ws = -1;  // workspace of the most recent encode call
     char err[256] = {0};
     std::mutex mu;
 };
@@ -231,6 +234,7 @@ DevBatch make_dev_batch(const slzw_params* params, const slzw_batch* b, const Wo
     a.retry_ids = (uint32_t*)w->retry.p;
     a.n_dev = nullptr;
     a.dec_tables = (uint32_t*)w->tables.p;
+    a.enc_tables = nullptr;
     a.p = *params;
     return a;
 }
@@ -270,6 +274,11 @@ int run_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, cu
         a.out_off = nullptr;
     }
     if (op == Op::Encode) {
+        if (const size_t tb = encode_table_bytes(a.n, ctx->num_sms)) {
+            CK(w->enc_tables.reserve(tb + 16384), "cudaMalloc(encode tables)");
+            a.enc_tables = (uint8_t*)(((uintptr_t)w->enc_tables.p + 16383) & ~(uintptr_t)16383);
+        }
+        ctx->last_encode_ws = (int)(w - ctx->ws);
         CK(encode_launch(a, ctx->num_sms, stream), "encode launch");
     } else {
         // fast kernel over the whole batch, then the exact kernel over whatever it deferred
@@ -680,6 +689,7 @@ void slzw_destroy(slzw_ctx* ctx) {
             w.order.release();
             w.retry.release();
             w.tables.release();
+            w.enc_tables.release();
             if (w.done) cudaEventDestroy(w.done);
         }
         for (int i = 0; i < kPipe; i++) ctx->pipe[i].release();
@@ -704,6 +714,18 @@ uint64_t slzw_last_deferred(slzw_ctx* ctx, uint32_t* ids, uint64_t cap) {
     if (ids && m && cudaMemcpy(ids, w.retry.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost) != cudaSuccess)
         return 0;
     return count;
+}
+
+int slzw_last_encode_shares(slzw_ctx* ctx, uint64_t bytes[4]) {
+    if (!ctx || !bytes || ctx->last_encode_ws < 0) return SLZW_RC_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
+    CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    CK(cudaMemcpy(bytes, (const unsigned long long*)ctx->ws[ctx->last_encode_ws].queue.p + 4,
+                  4 * sizeof(uint64_t), cudaMemcpyDeviceToHost),
+       "cudaMemcpy(encode shares)");
+    return SLZW_RC_OK;
 }
 
 int slzw_encode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,

@@ -27,6 +27,7 @@ struct DevBatch {
     uint32_t* retry_ids;            // fast decode: their ids
     const uint32_t* n_dev;          // exact decode of deferred streams: stream count on the device
     uint32_t* dec_tables;           // fast decode: 16 KB table blocks of the warps without a shared-memory table
+    uint8_t* enc_tables;            // encode: 16 KB dictionaries of the lanes in global memory (16 KB-aligned)
     slzw_params p;
 };
 
