@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libslzw.so")
+# SLZW_LIB: another build of the same library (tuning experiments, tools/build_variants.sh)
+LIB_PATH = os.environ.get("SLZW_LIB") or os.path.join(_HERE, "csrc", "libslzw.so")
 
 # slzw_status
 OK = 0

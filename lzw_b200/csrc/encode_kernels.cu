@@ -37,6 +37,10 @@
 #ifndef SLZW_U0
 #define SLZW_U0 4
 #endif
+#ifndef SLZW_HIT_REDUX
+#define SLZW_HIT_REDUX 1  // hit detection: one warp min-reduction (1) or ballot + find-first + shuffle (0)
+#endif
+
 
 namespace slzw {
 
@@ -52,6 +56,16 @@ static_assert(((kScr * kScrInv) & 0xFFFu) == 1u, "kScrInv must invert kScr mod 4
 
 __device__ __forceinline__ uint32_t scr(uint32_t code) { return (code * kScr) & 0xFFFu; }
 __device__ __forceinline__ uint32_t unscr(uint32_t code) { return (code * kScrInv) & 0xFFFu; }
+// The bucket lookups (match_tile_bucket) keep codes as q = code' - 1 mod 4096 and store slots
+// complemented, ~(key | q), so that an empty slot is still 0: slot ^ ~key is then below 4095
+// exactly for the slot that holds the key (q == 4095 would be code 0, which is never a dictionary
+// value; an empty slot gives ~key, at least 4095), so ONE warp reduction, min over the 32 slots of
+// slot ^ ~key, answers "found?" and returns the new prefix at once -- no compare + ballot +
+// find-first + shuffle (profiles/r02_encode_notes.md).
+template <bool Q>
+__device__ __forceinline__ uint32_t scrq(uint32_t code) { return (code * kScr - (Q ? 1u : 0u)) & 0xFFFu; }
+template <bool Q>
+__device__ __forceinline__ uint32_t unscrq(uint32_t e) { return (e * kScrInv + (Q ? kScrInv : 0u)) & 0xFFFu; }
 
 // Dictionary accesses by 32-bit shared-window address.  They are volatile asm statements so that
 // the compiler keeps them exactly where the match loop puts them (in particular the speculative
@@ -155,10 +169,14 @@ __device__ __forceinline__ uint32_t bfind(uint32_t v) {
     return r;
 }
 
-__device__ __forceinline__ void clear_table(uint32_t* table, int lane) {
+__device__ __forceinline__ void clear_table(uint32_t* table, int lane, uint32_t fill = 0u) {
 #pragma unroll 4
     for (int j = lane; j < kSlots / 4; j += kWarpSize)
-        reinterpret_cast<uint4*>(table)[j] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(table)[j] = make_uint4(fill, fill, fill, fill);
+    // the table accesses of the match loops are volatile asm statements without a memory clobber
+    // (a clobber makes the compiler reload the records around every lookup: 81 -> 91 ms at config
+    // 3); this keeps the plain stores above on their side of them
+    asm volatile("" ::: "memory");
 }
 
 // The match loop of encoder.rs:313-337 / 639-651 over the `len` byte records of one tile.
@@ -366,7 +384,9 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
 
 #define SLZW_STEP_B(RC)                                                                         \
     {                                                                                           \
-        const uint32_t key = t | (RC).x;                                                        \
+        /* slots hold ~(key | q): an empty slot is 0 and slot ^ ~key is q for the slot that   \
+           holds the key, at least 4095 for every other one */                                   \
+        const uint32_t key = ~(t | ((RC).x & 0xFF000u));                                        \
         uint32_t a = TMEM ? ((tp & 0x7Fu) ^ (RC).y) : (tlr | ((tp ^ (RC).y) & kBucketMask));    \
         /* Both bucket loads (tcgen05.ld, ldmatrix) are .sync.aligned: the warp is converged at   \
            every step, the compiler puts no divergence guard in front of the ballots and the     \
@@ -380,13 +400,24 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
             } else {                                                                            \
                 v = tbl_ld_bucket(a);                                                           \
             }                                                                                   \
-            const uint32_t x = v ^ key; /* == code' iff my slot holds the key */                \
-            const uint32_t bal = __ballot_sync(kFullMask, x - 1u < 4095u);                      \
-            if (bal) { /* find_word hit, encoder.rs:319-320 */                                  \
-                const uint32_t c = __shfl_sync(kFullMask, x, (int)bfind(bal));                  \
-                t = c << 20;                                                                    \
-                tp = TMEM ? c : c << 7;                                                         \
-                break;                                                                          \
+            /* q of the entry iff my slot holds the key, at least 4095 otherwise; the minimum   \
+               over the bucket (one REDUX) says "found" and is the new prefix */                 \
+            if (SLZW_HIT_REDUX) {                                                               \
+                const uint32_t c = __reduce_min_sync(kFullMask, v ^ key);                       \
+                if (c < 4095u) { /* find_word hit, encoder.rs:319-320 */                        \
+                    t = c << 20;                                                                \
+                    tp = TMEM ? c : c << 7;                                                     \
+                    break;                                                                      \
+                }                                                                               \
+            } else {                                                                            \
+                const uint32_t x = v ^ key;                                                     \
+                const uint32_t bal = __ballot_sync(kFullMask, x < 4095u);                       \
+                if (bal) {                                                                      \
+                    const uint32_t c = __shfl_sync(kFullMask, x, (int)bfind(bal));              \
+                    t = c << 20;                                                                \
+                    tp = TMEM ? c : c << 7;                                                     \
+                    break;                                                                      \
+                }                                                                               \
             }                                                                                   \
             const uint32_t em = __ballot_sync(kFullMask, v == 0u);                              \
             if (em == 0u) { /* full bucket: the key may have overflowed into the next one */    \
@@ -400,7 +431,7 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
             cpa += 2u;                                                                          \
             if (MODE == 0 || (MODE == 1 && (!FIXED || until != 0u))) {                          \
                 const bool mine = em == lanes_ge; /* I own the first empty slot */              \
-                const uint32_t entry = key | (ncs & 0xFFFu);                                    \
+                const uint32_t entry = key & ~(ncs & 0xFFFu);                                   \
                 if (TMEM) {                                                                     \
                     tmem_st(a, mine ? entry : v);                                               \
                     tmem_wait_st();                                                             \
@@ -418,25 +449,28 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                             until = nm - mask;                                                  \
                             mask = nm;                                                          \
                         } else { /* encoder.rs:329-333: clear at 12 bits, dictionary restarts */ \
-                            sts_u16(cpa, scr(clear_code) | (12u << 12));                        \
+                            sts_u16(cpa, scrq<true>(clear_code) | (12u << 12));                 \
                             cpa += 2u;                                                          \
                             ws = cs + 1u;                                                       \
                             wtag = ws << 12;                                                    \
                             mask = (1u << ws) - inc;                                            \
                             until = mask - first_code + 1u;                                     \
-                            ncs = scr(first_code);                                              \
+                            ncs = scrq<true>(first_code);                                       \
                             if (TMEM) {                                                         \
                                 tmem_clear(tb);                                                 \
                             } else {                                                            \
                                 __syncwarp();                                                   \
                                 clear_table(table, lane);                                       \
+                                __syncwarp();                                                   \
                             }                                                                   \
                         }                                                                       \
                     }                                                                           \
                 }                                                                               \
             }                                                                                   \
-            t = (RC).x * (kScr << 8); /* prefix = this byte: (k * kScr mod 4096) << 20 */       \
-            tp = TMEM ? t >> 20 : t >> 13;                                                      \
+            /* prefix = this byte: its q sits in the low bits of the record (only the low 7   \
+               bits of tp / bits 7..13 of tp << 7 reach the bucket address) */                   \
+            t = (RC).x << 20;                                                                   \
+            tp = TMEM ? ((RC).x & 0xFFFu) : (RC).x << 7;                                        \
             break;                                                                              \
         }                                                                                       \
     }
@@ -509,6 +543,7 @@ template <int TILE, bool FIXED, bool HAS_TMEM, int U, bool BS>
 __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restrict__ table,
                               const uint32_t tb, const bool tmem_warp, EncMisc<TILE>& S, int lane) {
     const bool TMEM = HAS_TMEM && tmem_warp;
+    constexpr bool Q = BS || HAS_TMEM;  // bucket lookups: codes as q = code' - 1, empty slots all ones
     using Misc = EncMisc<TILE>;
     static_assert(TILE % 4 == 0 && TILE <= 4 * kWarpSize, "one 32-bit word per lane");
     uint2* __restrict__ rec = S.rec;
@@ -555,7 +590,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
 
     MatchState m;
     m.t = 0;
-    m.ncs = scr(first_code);
+    m.ncs = scrq<Q>(first_code);
     m.ws = FIXED ? 12u : cs + 1;
     m.mask = (1u << m.ws) - inc;
     m.until = FIXED ? 4096u - first_code : m.mask - first_code + 1u;
@@ -571,7 +606,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     const uint64_t limit = cap > (~0ull - 7) / 8 ? ~0ull : cap * 8 + 7;
 
     auto push = [&](uint32_t code, uint32_t width) {  // BitWriter::write, io.rs:234-237, 296-300
-        codes[m.ncodes++] = (uint16_t)(scr(code) | (width << 12));
+        codes[m.ncodes++] = (uint16_t)(scrq<Q>(code) | (width << 12));
     };
 
     // Whole warp: bit-pack the buffered codes, flush complete words.
@@ -582,7 +617,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
             const uint32_t idx = base + lane;
             const uint32_t e = idx < count ? codes[idx] : 0u;
             const uint32_t wd = idx < count ? ((e >> 12) ? (e >> 12) : wdef) : 0u;
-            const uint32_t code = unscr(e) & ((1u << wd) - 1u);  // BitWriter masks to the width
+            const uint32_t code = unscrq<Q>(e) & ((1u << wd) - 1u);  // BitWriter masks to the width
             // inclusive prefix sum of the widths; codes without a tag all have the tile's width,
             // which is the common case (MODE 0 / 2 tiles) and needs no scan
             uint32_t x, total;
@@ -633,7 +668,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     if (!FIXED) push(clear_code, m.ws);  // encoder.rs:297
     if (n > 0) {
         const uint32_t first = __ldg(src);  // encoder.rs:311 / 637: not range-checked
-        m.t = scr(first) << 20;
+        m.t = scrq<Q>(first) << 20;
         if (!FIXED && n > 1 && first >= first_code) {
             // find_word would index past tree.nodes (encoder.rs:99) unless the second byte
             // is rejected first (encoder.rs:315-317)
@@ -661,7 +696,8 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
             const uint32_t k = (w >> (8 * b)) & 0xFFu;
             if (idx < tile_len) {
                 const uint32_t h7 = ((k * kByteMul) >> 2) & 0x7Fu;
-                rec[idx] = make_uint2(k << 12, TMEM ? (tb | h7)
+                // bucket lookups: the low 12 bits carry q of the byte itself (the prefix after a miss)
+                rec[idx] = make_uint2((k << 12) | (Q ? scrq<true>(k) : 0u), TMEM ? (tb | h7)
                                                : BS ? (h7 << 7)
                                                     : (tb | (((k * kByteMul) << 2) & kIdxMask4)));
                 if (!FIXED && k > max_code && idx < bad) bad = idx;
@@ -716,7 +752,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
             status = SLZW_ERR_IO_WRITE_ZERO;
         } else if (len < tile_len) {
             status = SLZW_ERR_UNEXPECTED_CODE;
-            detail = rec[len].x >> 12;
+            detail = (rec[len].x >> 12) & 0xFFu;
         }
         pos = npos;
         tile_len = nlen;
