@@ -128,7 +128,11 @@ typedef struct slzw_ctx slzw_ctx;
 /* ---- context ------------------------------------------------------------------------------
  * A context owns the per-device workspace (stream schedule, work queue, staging buffers).
  * One context per host thread; contexts are independent (the reference's functions are
- * stateless and re-entrant). */
+ * stateless and re-entrant).  The *_host entry points of one context run one at a
+ * time: a call that arrives while another one is running on the same context returns
+ * SLZW_RC_INVALID (its staging buffers are never interleaved); *_device calls of one context are
+ * serialised by a lock.  slzw_create fails with SLZW_RC_NO_DEVICE on anything but compute
+ * capability 10.0 (the kernels are sm_100a code). */
 SLZW_API int slzw_create(int device, slzw_ctx** ctx);
 SLZW_API void slzw_destroy(slzw_ctx* ctx);
 SLZW_API const char* slzw_last_error(const slzw_ctx* ctx);
@@ -158,7 +162,11 @@ SLZW_API int slzw_encode_batch_device(slzw_ctx* ctx, const slzw_params* params, 
 SLZW_API int slzw_decode_batch_device(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch,
                              void* cuda_stream);
 /* Host-resident batch: copies in, runs the device path, copies results back, synchronous.
- * Buffers from slzw_host_alloc() (pinned) overlap transfers with kernels. */
+ * Buffers from slzw_host_alloc() (pinned) overlap transfers with kernels.
+ * The whole capacity range out[out_off[0] .. out_off[n]) is copied back: bytes of a slot beyond
+ * out_len[i] are overwritten with unspecified values (the reference's `&mut [u8]` writer leaves
+ * them untouched), and an encode call moves the worst-case slots over the bus -- writers that
+ * want only the encoded bytes use slzw_encode_batch_host_dense. */
 SLZW_API int slzw_encode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch);
 SLZW_API int slzw_decode_batch_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* batch);
 

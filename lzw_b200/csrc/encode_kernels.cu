@@ -47,14 +47,12 @@ namespace slzw {
 namespace {
 
 constexpr int kSlots = 4096;
-constexpr uint32_t kIdxMask4 = (uint32_t)(kSlots - 1) << 2;  // byte offset of a slot
 constexpr uint32_t kBucketMask = 127u << 7;                   // byte offset of a 32-slot bucket
 constexpr uint32_t kScr = 0x9E5u;     // code -> code' = code * kScr mod 4096 (odd => bijection)
 constexpr uint32_t kScrInv = 0xBEDu;  // kScr * kScrInv == 1 mod 4096
 constexpr uint32_t kByteMul = 0x6A7u; // byte -> hash contribution
 static_assert(((kScr * kScrInv) & 0xFFFu) == 1u, "kScrInv must invert kScr mod 4096");
 
-__device__ __forceinline__ uint32_t scr(uint32_t code) { return (code * kScr) & 0xFFFu; }
 // The bucket lookups (match_tile_bucket) keep codes as q = code' - 1 mod 4096 and store slots
 // complemented, ~(key | q), so that an empty slot is still 0: slot ^ ~key is then below 4095
 // exactly for the slot that holds the key (q == 4095 would be code 0, which is never a dictionary
@@ -69,11 +67,6 @@ __device__ __forceinline__ uint32_t unscrq(uint32_t e) { return (e * kScrInv + (
 // Dictionary accesses by 32-bit shared-window address.  They are volatile asm statements so that
 // the compiler keeps them exactly where the match loop puts them (in particular the speculative
 // probe stays ahead of the branch it speculates on) and in order with each other.
-__device__ __forceinline__ uint32_t tbl_ld(uint32_t saddr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(saddr));
-    return v;
-}
 // One bucket (32 slots = 8 rows of 16 bytes) as a warp-collective matrix load: lanes 0..7 pass the
 // row addresses, lane i receives row i / 4, bytes 4 * (i % 4) .. + 3 -- slot i of the bucket, what
 // a per-lane 32-bit load would return.  The instruction is .aligned, which tells the compiler that
@@ -131,36 +124,6 @@ struct MatchState {
     uint32_t ncodes;  // codes buffered for the packer
 };
 
-// Collision path of the dictionary lookup.  The home slot (address `a`) held another key.
-// Every lane of the warp then looks at one of the next 32 slots of the linear-probing sequence;
-// two ballots give the first matching and the first empty slot, and whichever comes first decides
-// (an entry is never stored past an empty slot of its own probe sequence).  One shared-memory
-// wavefront resolves what would be up to 32 dependent probes, which is what lets the table run at
-// a load factor of 0.94 (4096 slots for <= 3838 entries).
-// Returns hit; `a` = address of the matching or of the empty slot, `s` = its word.
-__device__ __forceinline__ bool probe_wide(uint32_t tb, uint32_t key, int lane, uint32_t& a,
-                                           uint32_t& s) {
-    uint32_t h4 = a + 4u * (uint32_t)(lane + 1);  // this lane's slot in the first window
-    // the table always keeps empty slots (<= 4091 entries); the bound only keeps a corrupted
-    // table from hanging the warp
-#pragma unroll 1
-    for (int round = 0; round < kSlots / kWarpSize + 1; round++) {
-        const uint32_t v = tbl_ld(tb | (h4 & kIdxMask4));
-        const uint32_t bm = __ballot_sync(kFullMask, ((v ^ key) >> 12) == 0u && v != 0u);
-        const uint32_t be = __ballot_sync(kFullMask, v == 0u);
-        const uint32_t stop = bm | be;
-        if (stop) {
-            const int pos = __ffs(stop) - 1;
-            a = tb | (__shfl_sync(kFullMask, h4, pos) & kIdxMask4);
-            s = __shfl_sync(kFullMask, v, pos);
-            return (bm >> pos) & 1u;
-        }
-        h4 += 4u * kWarpSize;
-    }
-    s = 0u;
-    return false;
-}
-
 // index of the most significant set bit (FLO)
 __device__ __forceinline__ uint32_t bfind(uint32_t v) {
     uint32_t r;
@@ -176,125 +139,6 @@ __device__ __forceinline__ void clear_table(uint32_t* table, int lane, uint32_t 
     // (a clobber makes the compiler reload the records around every lookup: 81 -> 91 ms at config
     // 3); this keeps the plain stores above on their side of them
     asm volatile("" ::: "memory");
-}
-
-// The match loop of encoder.rs:313-337 / 639-651 over the `len` byte records of one tile.
-// rec[i] = {byte << 12, table base | hash contribution of the byte as a slot byte offset}.
-// The loop never leaves the tile early: input validation truncates the tile beforehand and the
-// capacity check happens per tile (see encode_stream).
-//
-template <bool FIXED, int U>
-__device__ __forceinline__ void match_tile(uint32_t* __restrict__ table, const uint32_t tb,
-                                           const uint2* __restrict__ rec,
-                                           uint16_t* __restrict__ codes, const int lane,
-                                           const uint32_t len, MatchState& m, const uint32_t cs,
-                                           const uint32_t inc, const uint32_t clear_code,
-                                           const uint32_t first_code) {
-    uint32_t t = m.t;
-    uint32_t ncs = m.ncs;
-    uint32_t ws = FIXED ? 12u : m.ws;
-    uint32_t wtag = ws << 12;
-    uint32_t mask = m.mask;
-    uint32_t until = m.until;
-    uint32_t cp = m.ncodes;
-    uint32_t i = 0;
-    uint2 r0;
-    uint32_t a, s;
-
-    // new index == mask (encoder.rs:326): width bump or clear + dictionary restart
-#define SLZW_BUMP()                                                                             \
-    {                                                                                           \
-        if (ws < 12u) { /* encoder.rs:327-328 */                                                \
-            ws++;                                                                               \
-            wtag = ws << 12;                                                                    \
-            const uint32_t nm = (1u << ws) - inc;                                               \
-            until = nm - mask;                                                                  \
-            mask = nm;                                                                          \
-        } else { /* encoder.rs:329-333: clear at 12 bits, dictionary restarts */                \
-            codes[cp++] = (uint16_t)(scr(clear_code) | (12u << 12));                            \
-            ws = cs + 1u;                                                                       \
-            wtag = ws << 12;                                                                    \
-            mask = (1u << ws) - inc;                                                            \
-            until = mask - first_code + 1u;                                                     \
-            ncs = scr(first_code);                                                              \
-            __syncwarp();                                                                       \
-            clear_table(table, lane);                                                           \
-            __syncwarp();                                                                       \
-        }                                                                                       \
-    }
-
-    // One byte of encoder.rs:313-337.  RC = record of this byte, RN = record
-    // of the next byte (anything addressable when this is the last byte of the tile: the
-    // lookahead is discarded).  On entry `s` is the word of the home slot `a` of the key (t, RC).
-#define SLZW_STEP(RC, RN)                                                                       \
-    {                                                                                           \
-        const uint32_t an = ((s << 2) & kIdxMask4) ^ (RN).y;                                    \
-        const uint32_t sn = tbl_ld(an);    /* speculative: assumes this byte hits */            \
-        const uint32_t x = s ^ t ^ (RC).x; /* == code' iff the slot holds this key */           \
-        if (x - 1u < 4095u) {              /* find_word hit, encoder.rs:319-320 */              \
-            t = s << 20;                                                                        \
-            s = sn;                                                                             \
-            a = an;                                                                             \
-        } else {                                                                                \
-            const uint32_t key = t | (RC).x;                                                    \
-            bool hit = false;                                                                   \
-            if (s != 0u) hit = probe_wide(tb, key, lane, a, s);                                 \
-            if (hit) {                                                                          \
-                t = s << 20;                                                                    \
-            } else {                                                                            \
-                /* miss: encoder.rs:322-324 / 645-649 */                                        \
-                codes[cp++] = (uint16_t)((t >> 20) | wtag);                                     \
-                if (!FIXED || until != 0u) {                                                    \
-                    tbl_st(a, key | ncs);                                                       \
-                    ncs = (ncs + kScr) & 0xFFFu;                                                \
-                    until--;                                                                    \
-                    if (!FIXED && until == 0u) SLZW_BUMP()                                      \
-                }                                                                               \
-                t = (RC).x * (kScr << 8); /* prefix = this byte: (k * kScr mod 4096) << 20 */   \
-            }                                                                                   \
-            a = ((t >> 18) & kIdxMask4) ^ (RN).y;                                               \
-            s = tbl_ld(a);                                                                      \
-        }                                                                                       \
-    }
-
-    r0 = rec[0];
-    a = (t >> 18) ^ r0.y;  // home slot of (prefix, byte 0); t >> 18 == prefix' << 2
-    s = tbl_ld(a);
-    // U = unrolling of the step (loop overhead against instruction-cache footprint)
-    if constexpr (U >= 4) {
-        while (i + 4u <= len) {
-            const uint2 r1 = rec[i + 1], r2 = rec[i + 2], r3 = rec[i + 3], r4 = rec[i + 4];
-            SLZW_STEP(r0, r1)
-            SLZW_STEP(r1, r2)
-            SLZW_STEP(r2, r3)
-            SLZW_STEP(r3, r4)
-            r0 = r4;
-            i += 4u;
-        }
-    } else if constexpr (U >= 2) {
-        while (i + 2u <= len) {
-            const uint2 r1 = rec[i + 1], r2 = rec[i + 2];
-            SLZW_STEP(r0, r1)
-            SLZW_STEP(r1, r2)
-            r0 = r2;
-            i += 2u;
-        }
-    }
-#pragma unroll 1
-    while (i < len) {
-        const uint2 r1 = rec[i + 1];
-        SLZW_STEP(r0, r1)
-        r0 = r1;
-        i += 1u;
-    }
-#undef SLZW_STEP
-#undef SLZW_BUMP
-    m.t = t;
-    m.ncs = ncs;
-    m.ws = ws;
-    m.mask = mask;
-    m.until = until;
-    m.ncodes = cp;
 }
 
 // ---- tensor memory as a second dictionary store ------------------------------------------------
@@ -538,11 +382,10 @@ __device__ __forceinline__ uint32_t load_tile_word(const uint8_t* __restrict__ p
 // unused); otherwise `table` / `tb` are the generic pointer and the shared-window address of its
 // 16 KB.  One function body for both kinds of warp: everything but the match loop is shared, which
 // keeps the instruction footprint of the 28 warps down.
-template <int TILE, bool FIXED, bool HAS_TMEM, int U, bool BS>
+template <int TILE, bool FIXED, bool HAS_TMEM, int U>
 __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restrict__ table,
                               const uint32_t tb, const bool tmem_warp, EncMisc<TILE>& S, int lane) {
     const bool TMEM = HAS_TMEM && tmem_warp;
-    constexpr bool Q = BS || HAS_TMEM;  // bucket lookups: codes as q = code' - 1, empty slots all ones
     using Misc = EncMisc<TILE>;
     static_assert(TILE % 4 == 0 && TILE <= 4 * kWarpSize, "one 32-bit word per lane");
     uint2* __restrict__ rec = S.rec;
@@ -589,7 +432,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
 
     MatchState m;
     m.t = 0;
-    m.ncs = scrq<Q>(first_code);
+    m.ncs = scrq<true>(first_code);
     m.ws = FIXED ? 12u : cs + 1;
     m.mask = (1u << m.ws) - inc;
     m.until = FIXED ? 4096u - first_code : m.mask - first_code + 1u;
@@ -605,7 +448,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     const uint64_t limit = cap > (~0ull - 7) / 8 ? ~0ull : cap * 8 + 7;
 
     auto push = [&](uint32_t code, uint32_t width) {  // BitWriter::write, io.rs:234-237, 296-300
-        codes[m.ncodes++] = (uint16_t)(scrq<Q>(code) | (width << 12));
+        codes[m.ncodes++] = (uint16_t)(scrq<true>(code) | (width << 12));
     };
 
     // Whole warp: bit-pack the buffered codes, flush complete words.
@@ -616,7 +459,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
             const uint32_t idx = base + lane;
             const uint32_t e = idx < count ? codes[idx] : 0u;
             const uint32_t wd = idx < count ? ((e >> 12) ? (e >> 12) : wdef) : 0u;
-            const uint32_t code = unscrq<Q>(e) & ((1u << wd) - 1u);  // BitWriter masks to the width
+            const uint32_t code = unscrq<true>(e) & ((1u << wd) - 1u);  // BitWriter masks to the width
             // inclusive prefix sum of the widths; codes without a tag all have the tile's width,
             // which is the common case (MODE 0 / 2 tiles) and needs no scan
             uint32_t x, total;
@@ -667,7 +510,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     if (!FIXED) push(clear_code, m.ws);  // encoder.rs:297
     if (n > 0) {
         const uint32_t first = __ldg(src);  // encoder.rs:311 / 637: not range-checked
-        m.t = scrq<Q>(first) << 20;
+        m.t = scrq<true>(first) << 20;
         if (!FIXED && n > 1 && first >= first_code) {
             // find_word would index past tree.nodes (encoder.rs:99) unless the second byte
             // is rejected first (encoder.rs:315-317)
@@ -696,9 +539,8 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
             if (idx < tile_len) {
                 const uint32_t h7 = ((k * kByteMul) >> 2) & 0x7Fu;
                 // bucket lookups: the low 12 bits carry q of the byte itself (the prefix after a miss)
-                rec[idx] = make_uint2((k << 12) | (Q ? scrq<true>(k) : 0u), TMEM ? (tb | h7)
-                                               : BS ? (h7 << 7)
-                                                    : (tb | (((k * kByteMul) << 2) & kIdxMask4)));
+                rec[idx] = make_uint2((k << 12) | scrq<true>(k), TMEM ? (tb | h7)
+                                               : (h7 << 7));
                 if (!FIXED && k > max_code && idx < bad) bad = idx;
             }
         }
@@ -731,12 +573,10 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
                 if (mode == 0) SLZW_MATCH_B(true, 0);
                 else if (mode == 1) SLZW_MATCH_B(true, 1);
                 else if constexpr (FIXED) SLZW_MATCH_B(true, 2);
-            } else if constexpr (BS) {
+            } else {
                 if (mode == 0) SLZW_MATCH_B(false, 0);
                 else if (mode == 1) SLZW_MATCH_B(false, 1);
                 else if constexpr (FIXED) SLZW_MATCH_B(false, 2);
-            } else {
-                match_tile<FIXED, U>(table, tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
             }
 #undef SLZW_MATCH_B
         }
@@ -826,7 +666,7 @@ struct EncLayout {
 
 // Warps [0, TWARPS) keep their dictionary in tensor memory, warps [TWARPS, TWARPS + SWARPS) in
 // shared memory.
-template <int TILE, int SWARPS, int TWARPS, int U, bool BS, bool FIXED>
+template <int TILE, int SWARPS, int TWARPS, int U, bool FIXED>
 __global__ void __launch_bounds__((SWARPS + TWARPS) * kWarpSize, 1)
 slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -870,7 +710,7 @@ slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= a.n) break;
         const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-        encode_stream<TILE, FIXED, (TWARPS > 0), U, BS>(a, sid, table, tb, tmem_warp, S, lane);
+        encode_stream<TILE, FIXED, (TWARPS > 0), U>(a, sid, table, tb, tmem_warp, S, lane);
     }
 
     if constexpr (TWARPS > 0) {
@@ -890,7 +730,7 @@ slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
 
 // ---- launch configuration ---------------------------------------------------------------------
 // {input tile, warps with a shared-memory dictionary, warps with a tensor-memory dictionary}
-template <int TILE, int SWARPS, int TWARPS, int U, bool BS>
+template <int TILE, int SWARPS, int TWARPS, int U>
 struct EncConfig {
     using L = EncLayout<TILE, SWARPS, SWARPS + TWARPS>;
     // the shared window of a CTA starts with 1 KB reserved by the system; taking the larger of
@@ -900,10 +740,10 @@ struct EncConfig {
         return (a > b ? a : b) + L::kHead;
     }
     static cudaError_t configure() {
-        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, BS, false>,
+        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, BS, true>,
+        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
     }
     static cudaError_t launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
@@ -911,9 +751,9 @@ struct EncConfig {
         const uint64_t ctas = (a.n + WARPS - 1) / WARPS;
         const int grid = (int)(ctas < (uint64_t)num_sms ? ctas : (uint64_t)num_sms);
         if (a.p.flavour == SLZW_FLAVOUR_FIXED)
-            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, BS, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         else
-            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, BS, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         return cudaGetLastError();
     }
 };
@@ -922,37 +762,33 @@ struct EncConfig {
 #include "exp/encode_lanes_config.cuh"
 #endif
 
-// {input tile, shared-memory dictionaries, tensor-memory dictionaries, step unrolling,
-//  bucket lookups in shared memory (tensor memory always uses them)}
-using Enc0 = EncConfig<96, 12, 16, 2, true>;    // 28 streams per SM, one warp each, bucket lookups
-using Enc1 = EncConfig<128, 12, 0, 4, false>;   // shared memory only, scalar speculative probes
-static int g_enc_config = -1;
-
-void encode_select_config(int c) { g_enc_config = c; }
+// {input tile, shared-memory dictionaries, tensor-memory dictionaries, step unrolling}: 28 streams
+// per SM, one warp each.  Round 1 kept a second configuration (scalar speculative probes, 12 warps)
+// for batches with few streams; with the min-reduction lookups this one is faster there too
+// (config 4, 512 frames of 1 MiB: 148.7 against 171.9 ms), so every batch takes the same kernel.
+using Enc0 = EncConfig<96, 12, 16, 2>;
 
 #ifndef SLZW_LANE_CONFIGS
 #define SLZW_LANE_CONFIGS(X)  // experiment configurations (exp/encode_lanes_config.cuh) are not built in
 #endif
+static int g_enc_config = 0;
+
+// tuning experiments only (SLZW_ENC_CONFIG): the configurations of exp/ when they are built in
+void encode_select_config(int c) { g_enc_config = c; }
 
 cudaError_t encode_configure() {
     cudaError_t e = Enc0::configure();
     if (e != cudaSuccess) return e;
-    if ((e = Enc1::configure()) != cudaSuccess) return e;
 #define X(id, C) if ((e = C::configure()) != cudaSuccess) return e;
     SLZW_LANE_CONFIGS(X)
 #undef X
     return cudaSuccess;
 }
 
-static int encode_pick(uint64_t n, int num_sms) {
-    int cfg = g_enc_config;
-    if (cfg < 0) cfg = n <= (uint64_t)num_sms * 12u ? 1 : 0;
-    return cfg;
-}
-
-// global-memory dictionaries the launch needs (0 for the configurations without such lanes)
-size_t encode_table_bytes(uint64_t n, int num_sms) {
-    switch (encode_pick(n, num_sms)) {
+// global-memory dictionaries the launch needs (none outside the experiments)
+size_t encode_table_bytes(uint64_t, int num_sms) {
+    (void)num_sms;
+    switch (g_enc_config) {
 #define X(id, C) case id: return C::table_bytes(num_sms);
         SLZW_LANE_CONFIGS(X)
 #undef X
@@ -961,8 +797,7 @@ size_t encode_table_bytes(uint64_t n, int num_sms) {
 }
 
 cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
-    switch (encode_pick(a.n, num_sms)) {
-        case 1: return Enc1::launch(a, num_sms, stream);
+    switch (g_enc_config) {
 #define X(id, C) case id: return C::launch(a, num_sms, stream);
         SLZW_LANE_CONFIGS(X)
 #undef X

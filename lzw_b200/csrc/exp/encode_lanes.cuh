@@ -23,6 +23,7 @@
 // cp.async fills RCH - 1 chunks of 16 bytes ahead of the lane (no registers, no stall).  Rare events
 // (stream start / end, width bump, dictionary reset, errors) raise a per-lane flag and are served
 // between iterations; dictionary clears are done by the whole warp.
+__device__ __forceinline__ uint32_t scr(uint32_t code) { return (code * kScr) & 0xFFFu; }
 __device__ __forceinline__ uint32_t unscr(uint32_t code) { return (code * kScrInv) & 0xFFFu; }
 constexpr uint32_t kLaneBucketMask = 0x3FE0u;  // byte offset of a 32-byte bucket inside a table
 constexpr uint32_t kLaneHashMul = 0x6A7u << 5;  // byte -> bucket byte offset

@@ -96,7 +96,7 @@ slzw_encode_lanes_kernel(const DevBatch a, const uint32_t dyn_bytes) {
                 q = __shfl_sync(kFullMask, q, 0);
                 if (q >= a.n) break;
                 const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-                encode_stream<TILE, FIXED, (TWARPS > 0), 2, true>(a, sid, table, tb, tmem_warp, S, lane);
+                encode_stream<TILE, FIXED, (TWARPS > 0), 2>(a, sid, table, tb, tmem_warp, S, lane);
                 if (lane == 0) atomicAdd(a.queue + (tmem_warp ? 4 : 5), a.in_off[sid + 1] - a.in_off[sid]);
             }
         }

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -149,6 +150,9 @@ struct slzw_ctx {
     int last_encode_ws = -1;  // workspace of the most recent encode call
     char err[256] = {0};
     std::mutex mu;
+    // the staging slots of the host entry points belong to one call at a time: a second call on
+    // the same context while one is running is refused (SLZW_RC_INVALID), not interleaved
+    std::atomic<bool> host_busy{false};
 };
 
 namespace {
@@ -175,6 +179,19 @@ struct DeviceGuard {
     ~DeviceGuard() {
         int cur = -1;
         if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+// One host-path call per context at a time.
+struct HostCallGuard {
+    slzw_ctx* ctx;
+    bool ok;
+    explicit HostCallGuard(slzw_ctx* c) : ctx(c), ok(c && !c->host_busy.exchange(true, std::memory_order_acquire)) {
+        if (c && !ok)
+            snprintf(c->err, sizeof c->err, "context is in use by another host call (one context per thread)");
+    }
+    ~HostCallGuard() {
+        if (ok) ctx->host_busy.store(false, std::memory_order_release);
     }
 };
 
@@ -373,6 +390,8 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
     }
     const uint64_t n = b->n;
     if (n == 0) return SLZW_RC_OK;
+    HostCallGuard busy(ctx);
+    if (!busy.ok) return SLZW_RC_INVALID;
     const bool needs_out = op != Op::DecodedSizes;
     if (!b->in_off || !b->out_len || !b->status || !b->detail ||
         (needs_out && (!b->out || !b->out_off)) || (b->in_off[n] > 0 && !b->in)) {
@@ -494,6 +513,8 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     out_off[0] = 0;
     if (needed) *needed = 0;
     if (n == 0) return SLZW_RC_OK;
+    HostCallGuard busy(ctx);
+    if (!busy.ok) return SLZW_RC_INVALID;
     if (align == 0) align = 1;
     NvtxRange range("slzw encode batch, dense (host pipeline)");
     DeviceGuard guard(ctx->device);
@@ -649,7 +670,9 @@ int slzw_create(int device, slzw_ctx** out) {
     if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return SLZW_RC_NO_DEVICE;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SLZW_RC_NO_DEVICE;
-    if (prop.major != 10) return SLZW_RC_NO_DEVICE;  // kernels are built for sm_100a only
+    // the kernels are built for sm_100a only, which has no forward-compatible PTX (sm_101 / sm_103
+    // parts cannot run them)
+    if (prop.major != 10 || prop.minor != 0) return SLZW_RC_NO_DEVICE;
     slzw_ctx* ctx = new (std::nothrow) slzw_ctx;
     if (!ctx) return SLZW_RC_NOMEM;
     ctx->device = device;

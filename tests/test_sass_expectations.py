@@ -1,6 +1,6 @@
 """What the design relies on in the generated code, checked on the built objects with cuobjdump
 (no GPU needed): the default encoder kernel keeps its dictionaries in tensor memory and shared
-memory (LDTM / STTM / LDSM), nothing spills to local memory in the codec kernels, and the
+memory (LDTM / STTM / LDSM), finds a key with one warp reduction (REDUX), nothing spills to local memory in the codec kernels, and the
 shared-memory lookup step carries no divergence guard (profiles/r01_encode_notes.md)."""
 import os
 import re
@@ -42,14 +42,16 @@ def _ops(lines):
 
 def test_default_encoder_uses_tensor_memory_and_matrix_loads():
     funcs = _functions("encode_kernels.o")
-    # slzw_encode_kernel<96, 12, 16, 2, true, FIXED>
-    default = {n: l for n, l in funcs.items() if "slzw_encode_kernelILi96ELi12ELi16ELi2ELb1E" in n}
+    # slzw_encode_kernel<96, 12, 16, 2, FIXED>: the one encoder kernel of the library
+    default = {n: l for n, l in funcs.items() if "slzw_encode_kernelILi96ELi12ELi16ELi2ELb" in n}
     assert len(default) == 2
+    assert len([n for n in funcs if "slzw_encode" in n]) == 2  # no experiment kernels in the product build
     for name, lines in default.items():
         ops = _ops(lines)
         assert any(o.startswith("LDTM") for o in ops), name          # tcgen05.ld
         assert any(o.startswith("STTM") for o in ops), name          # tcgen05.st
         assert any(o.startswith("LDSM") for o in ops), name          # ldmatrix bucket loads
+        assert any("REDUX" in o for o in ops), name                  # hit detection: one warp min-reduction
         assert not any(o.startswith(("LDL", "STL")) for o in ops), name  # no spills
         # the instruction after an LDSM-based lookup reaches its ballot without a divergence guard
         idx = [i for i, o in enumerate(ops) if o.startswith("LDSM")]
