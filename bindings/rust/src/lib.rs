@@ -3,56 +3,9 @@
 //! associated functions, same error enums, plus `encode_batch` / `decode_batch`.
 //! NOT compiled in this repository's image (no Rust toolchain); see INTEGRATION.md.
 use std::io::{self, Read, Write};
-use std::os::raw::{c_char, c_int, c_void};
 
-#[repr(C)]
-#[derive(Clone, Copy)]
-pub struct SlzwParams {
-    pub flavour: u8,
-    pub code_size: u8,
-    pub big_endian: u8,
-    pub tiff_early_change: u8,
-}
-
-#[repr(C)]
-pub struct SlzwBatch {
-    pub input: *const u8,
-    pub in_off: *const u64,
-    pub out: *mut u8,
-    pub out_off: *const u64,
-    pub out_len: *mut u64,
-    pub status: *mut u32,
-    pub detail: *mut u32,
-    pub code_size: *const u8,
-    pub n: u64,
-}
-
-#[repr(C)]
-pub struct SlzwCtx {
-    _private: [u8; 0],
-}
-
-extern "C" {
-    fn slzw_create(device: c_int, ctx: *mut *mut SlzwCtx) -> c_int;
-    fn slzw_destroy(ctx: *mut SlzwCtx);
-    fn slzw_last_error(ctx: *const SlzwCtx) -> *const c_char;
-    fn slzw_encode(ctx: *mut SlzwCtx, p: *const SlzwParams, input: *const u8, n: u64, out: *mut u8,
-                   cap: u64, out_len: *mut u64, detail: *mut u32) -> c_int;
-    fn slzw_decode(ctx: *mut SlzwCtx, p: *const SlzwParams, input: *const u8, n: u64, out: *mut u8,
-                   cap: u64, out_len: *mut u64, detail: *mut u32) -> c_int;
-    fn slzw_encode_bound(p: *const SlzwParams, n: u64) -> u64;
-    fn slzw_encode_batch_host(ctx: *mut SlzwCtx, p: *const SlzwParams, b: *const SlzwBatch) -> c_int;
-    fn slzw_decode_batch_host(ctx: *mut SlzwCtx, p: *const SlzwParams, b: *const SlzwBatch) -> c_int;
-    fn slzw_encode_batch_device(ctx: *mut SlzwCtx, p: *const SlzwParams, b: *const SlzwBatch,
-                                cuda_stream: *mut c_void) -> c_int;
-    fn slzw_decode_batch_device(ctx: *mut SlzwCtx, p: *const SlzwParams, b: *const SlzwBatch,
-                                cuda_stream: *mut c_void) -> c_int;
-    #[allow(dead_code)]
-    fn slzw_decoded_sizes_batch_host(ctx: *mut SlzwCtx, p: *const SlzwParams, b: *const SlzwBatch) -> c_int;
-    /// TIFF Predictor = 2 inside the host batch calls (0, 0 = off)
-    #[allow(dead_code)]
-    fn slzw_set_tiff_predictor(ctx: *mut SlzwCtx, row_bytes: u32, samples_per_pixel: u32) -> c_int;
-}
+pub mod ffi;
+use ffi::*;
 
 /// lzw/src/lib.rs:59-65
 #[derive(Clone, Copy, Debug, PartialEq, Eq)]

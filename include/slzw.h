@@ -183,6 +183,19 @@ SLZW_API int slzw_encode_batch_host_dense(slzw_ctx* ctx, const slzw_params* para
                                           uint8_t* out_dense, uint64_t out_cap, uint64_t* out_off,
                                           uint32_t* status, uint32_t* detail, uint64_t* needed);
 
+/* The same in two phases, for callers that have to know the encoded size before they can say
+ * where the bytes go (a writer that allocates exactly; several devices filling one dense buffer,
+ * slzw_multi_*).  _begin encodes and compacts; the encoded bytes stay on the device, out_off[n+1]
+ * (relative to the first stream, out_off[0] = 0), status and detail come back and *total receives
+ * out_off[n].  _finish copies the `total` bytes to out_dense (SLZW_RC_NOMEM if out_cap is smaller;
+ * the bytes then stay available for another _finish).  A new _begin discards what an earlier one
+ * left behind. */
+SLZW_API int slzw_encode_batch_host_dense_begin(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
+                                       const uint64_t* in_off, uint64_t n, const uint8_t* code_size,
+                                       uint64_t align, uint64_t* out_off, uint32_t* status,
+                                       uint32_t* detail, uint64_t* total);
+SLZW_API int slzw_encode_batch_host_dense_finish(slzw_ctx* ctx, uint8_t* out_dense, uint64_t out_cap);
+
 /* ---- single stream (= batch of one): backs the 16 facade functions ------------------------
  * Returns SLZW_RC_* (<0) on launch failure, otherwise the stream's slzw_status (>=0). */
 SLZW_API int slzw_encode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,
@@ -237,6 +250,34 @@ SLZW_API void slzw_host_free(void* p);
  * e.g. "Code size must be between 2 and 8, was 10." ; returns bytes written (excl. NUL). */
 SLZW_API int slzw_status_message(int is_decoder, uint32_t status, uint32_t detail, uint8_t code_size,
                         char* buf, size_t buf_len);
+
+/* ---- one host batch over several GPUs of one box ----------------------------------------------
+ * Streams are independent, so a batch shards by stream: contiguous ranges balanced by bytes, one
+ * context and one worker thread per device, no exchange between devices; sizes and statuses are
+ * gathered on the host.  Results are identical to the single-device calls (each stream is encoded /
+ * decoded on its own, lzw/src/encoder.rs:273-346, decoder.rs:174-290).  The reference's API is one
+ * call per job (lzw/src/lib.rs:51-91); these are that call for a box. */
+typedef struct slzw_multi slzw_multi;
+/* devices == NULL: the first n_devices visible devices (all of them if n_devices <= 0). */
+SLZW_API int slzw_multi_create(const int* devices, int n_devices, slzw_multi** out);
+SLZW_API void slzw_multi_destroy(slzw_multi* m);
+SLZW_API int slzw_multi_device_count(const slzw_multi* m);
+SLZW_API const char* slzw_multi_last_error(const slzw_multi* m);
+SLZW_API uint64_t slzw_multi_kernel_launches(const slzw_multi* m);
+/* bounds[0 .. parts]: streams [bounds[p], bounds[p+1]) go to part p; the parts are contiguous and
+ * balanced by weight_off[i+1] - weight_off[i] (bytes).  The partition the calls below use. */
+SLZW_API void slzw_partition_streams(const uint64_t* weight_off, uint64_t n, int parts, uint64_t* bounds);
+/* slzw_encode_batch_host / slzw_decode_batch_host / slzw_encode_batch_host_dense with the batch
+ * spread over the devices of `m` (encode: balanced by input bytes; decode: by the capacity slots).
+ * The dense variant places the shards back to back: every device encodes and compacts its shard,
+ * the host adds up the sizes, then every device copies its bytes to their final place. */
+SLZW_API int slzw_multi_encode_batch_host(slzw_multi* m, const slzw_params* params, const slzw_batch* batch);
+SLZW_API int slzw_multi_decode_batch_host(slzw_multi* m, const slzw_params* params, const slzw_batch* batch);
+SLZW_API int slzw_multi_encode_batch_host_dense(slzw_multi* m, const slzw_params* params, const uint8_t* in,
+                                       const uint64_t* in_off, uint64_t n, const uint8_t* code_size,
+                                       uint64_t align, uint8_t* out_dense, uint64_t out_cap,
+                                       uint64_t* out_off, uint32_t* status, uint32_t* detail,
+                                       uint64_t* needed);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@ Host-side mirror of the reference's public interface (/root/reference/lzw/src/li
 (`Codec`) the reference lacks.  Everything computes on the GPU through libslzw.so.
 """
 from .types import CodeSizeStrategy, Endianness  # noqa: F401
-from .codec import Codec, PinnedBuffer, default_codec  # noqa: F401
+from .codec import Codec, MultiCodec, PinnedBuffer, default_codec, partition_streams  # noqa: F401
 from . import decoder, encoder  # noqa: F401
 
-__all__ = ["Endianness", "CodeSizeStrategy", "Codec", "PinnedBuffer", "default_codec", "encoder", "decoder"]
+__all__ = ["Endianness", "CodeSizeStrategy", "Codec", "MultiCodec", "partition_streams", "PinnedBuffer", "default_codec", "encoder", "decoder"]

@@ -80,6 +80,22 @@ SYMBOLS = {
                                                C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
                                                C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
                                                _P(C.c_uint64)]),
+    "slzw_encode_batch_host_dense_begin": (C.c_int, [C.c_void_p, _P(Params), C.c_void_p, C.c_void_p,
+                                                     C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p, _P(C.c_uint64)]),
+    "slzw_encode_batch_host_dense_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "slzw_multi_create": (C.c_int, [C.c_void_p, C.c_int, _P(C.c_void_p)]),
+    "slzw_multi_destroy": (None, [C.c_void_p]),
+    "slzw_multi_device_count": (C.c_int, [C.c_void_p]),
+    "slzw_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "slzw_multi_kernel_launches": (C.c_uint64, [C.c_void_p]),
+    "slzw_partition_streams": (None, [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "slzw_multi_encode_batch_host": (C.c_int, [C.c_void_p, _P(Params), _P(Batch)]),
+    "slzw_multi_decode_batch_host": (C.c_int, [C.c_void_p, _P(Params), _P(Batch)]),
+    "slzw_multi_encode_batch_host_dense": (C.c_int, [C.c_void_p, _P(Params), C.c_void_p, C.c_void_p,
+                                                     C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p,
+                                                     C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                     _P(C.c_uint64)]),
     "slzw_encode": (C.c_int, [C.c_void_p, _P(Params), C.c_void_p, C.c_uint64, C.c_void_p,
                               C.c_uint64, _P(C.c_uint64), _P(C.c_uint32)]),
     "slzw_decode": (C.c_int, [C.c_void_p, _P(Params), C.c_void_p, C.c_uint64, C.c_void_p,

@@ -172,6 +172,28 @@ class Codec:
         self._check(rc, "slzw_encode_batch_host_dense")
         return out[: int(out_off[-1])], out_off, status[:n], detail[:n]
 
+    def encode_batch_dense_begin(self, params, in_buf, in_off, code_size=None, align=1):
+        """First phase of the two-phase dense encode: returns (dense_off, status, detail, total);
+        the encoded bytes stay on the device until encode_batch_dense_finish."""
+        in_buf = np.ascontiguousarray(in_buf, dtype=np.uint8)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        n = in_off.size - 1
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.uint32)
+        detail = np.zeros(max(n, 1), dtype=np.uint32)
+        cs = None if code_size is None else np.ascontiguousarray(code_size, dtype=np.uint8)
+        total = C.c_uint64(0)
+        self._check(self._lib.slzw_encode_batch_host_dense_begin(
+            self._h, C.byref(params), in_buf.ctypes.data, in_off.ctypes.data, n,
+            None if cs is None else cs.ctypes.data, align, out_off.ctypes.data, status.ctypes.data,
+            detail.ctypes.data, C.byref(total)), "slzw_encode_batch_host_dense_begin")
+        return out_off, status[:n], detail[:n], int(total.value)
+
+    def encode_batch_dense_finish(self, out):
+        self._check(self._lib.slzw_encode_batch_host_dense_finish(self._h, out.ctypes.data, out.size),
+                    "slzw_encode_batch_host_dense_finish")
+        return out
+
     def decode_batch(self, params, in_buf, in_off, out_off, code_size=None, out=None):
         """Decodes streams into capacity slots out_off.  `out` may be a preallocated (pinned) uint8
         array.  Returns (out, out_len, status, detail)."""
@@ -219,6 +241,104 @@ class Codec:
 
     def status_message(self, is_decoder: bool, status: int, detail: int, code_size: int = 0) -> str:
         return status_message(is_decoder, status, detail, code_size)
+
+
+class MultiCodec:
+    """One host batch over several GPUs of one box (slzw_multi_*): the batch is sharded by stream,
+    one context and one worker thread per device, no exchange between devices; results are those
+    of the single-device calls."""
+
+    def __init__(self, devices=None, n_devices: int = 0):
+        self._lib = _lib.lib()
+        h = C.c_void_p()
+        if devices is None:
+            rc = self._lib.slzw_multi_create(None, n_devices, C.byref(h))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self._lib.slzw_multi_create(arr, len(devices), C.byref(h))
+        if rc != _lib.RC_OK:
+            raise SlzwError(f"slzw_multi_create failed with rc={rc}"
+                            + (": no usable sm_100 CUDA device -- lzw_b200 has no CPU fallback"
+                               if rc == _lib.RC_NO_DEVICE else ""))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.slzw_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_count(self) -> int:
+        return int(self._lib.slzw_multi_device_count(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.slzw_multi_kernel_launches(self._h))
+
+    def _check(self, rc, what):
+        if rc != _lib.RC_OK:
+            raise SlzwError(f"{what} failed (rc={rc}): {self._lib.slzw_multi_last_error(self._h).decode()}")
+
+    def _host(self, fn, params, in_buf, in_off, out_off, code_size, what, out=None):
+        in_buf = np.ascontiguousarray(in_buf, dtype=np.uint8)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+        n = in_off.size - 1
+        if out is None:
+            out = np.zeros(max(int(out_off[-1]), 1), dtype=np.uint8)
+        out_len = np.zeros(max(n, 1), dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.uint32)
+        detail = np.zeros(max(n, 1), dtype=np.uint32)
+        cs = None if code_size is None else np.ascontiguousarray(code_size, dtype=np.uint8)
+        b = Batch(in_buf.ctypes.data, in_off.ctypes.data, out.ctypes.data, out_off.ctypes.data,
+                  out_len.ctypes.data, status.ctypes.data, detail.ctypes.data,
+                  None if cs is None else cs.ctypes.data, n)
+        self._check(fn(self._h, C.byref(params), C.byref(b)), what)
+        return out, out_len[:n], status[:n], detail[:n]
+
+    def encode_batch(self, params, in_buf, in_off, out_off, code_size=None, out=None):
+        """Returns (out, out_len, status, detail) for capacity slots out_off."""
+        return self._host(self._lib.slzw_multi_encode_batch_host, params, in_buf, in_off, out_off, code_size,
+                          "slzw_multi_encode_batch_host", out=out)
+
+    def decode_batch(self, params, in_buf, in_off, out_off, code_size=None, out=None):
+        return self._host(self._lib.slzw_multi_decode_batch_host, params, in_buf, in_off, out_off, code_size,
+                          "slzw_multi_decode_batch_host", out=out)
+
+    def encode_batch_dense(self, params, in_buf, in_off, code_size=None, align=1, out=None):
+        """Returns (dense, dense_off, status, detail); the shards of the devices lie back to back."""
+        in_buf = np.ascontiguousarray(in_buf, dtype=np.uint8)
+        in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+        n = in_off.size - 1
+        if out is None:
+            lens = np.diff(in_off)
+            worst = int((((lens + 3 + lens // 3838 + 1) * 12 + 7) // 8 + align).sum())
+            out = np.empty(max(worst, 1), dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(max(n, 1), dtype=np.uint32)
+        detail = np.zeros(max(n, 1), dtype=np.uint32)
+        cs = None if code_size is None else np.ascontiguousarray(code_size, dtype=np.uint8)
+        needed = C.c_uint64(0)
+        rc = self._lib.slzw_multi_encode_batch_host_dense(
+            self._h, C.byref(params), in_buf.ctypes.data, in_off.ctypes.data, n,
+            None if cs is None else cs.ctypes.data, align, out.ctypes.data, out.size,
+            out_off.ctypes.data, status.ctypes.data, detail.ctypes.data, C.byref(needed))
+        self._check(rc, "slzw_multi_encode_batch_host_dense")
+        return out[: int(out_off[-1])], out_off, status[:n], detail[:n]
+
+
+def partition_streams(off, parts: int) -> np.ndarray:
+    """slzw_partition_streams: contiguous stream ranges balanced by bytes (parts + 1 bounds)."""
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    bounds = np.zeros(parts + 1, dtype=np.uint64)
+    _lib.lib().slzw_partition_streams(off.ctypes.data, off.size - 1, parts, bounds.ctypes.data)
+    return bounds
 
 
 class PinnedBuffer:

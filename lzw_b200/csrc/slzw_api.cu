@@ -153,6 +153,12 @@ struct slzw_ctx {
     // the staging slots of the host entry points belong to one call at a time: a second call on
     // the same context while one is running is refused (SLZW_RC_INVALID), not interleaved
     std::atomic<bool> host_busy{false};
+    // two-phase dense encode (slzw_encode_batch_host_dense_begin / _finish): the encoded chunks stay
+    // on the device until the caller knows where they go
+    DevBuf shard_dense;
+    struct DeferredChunk { uint64_t dev_off, bytes; };
+    std::vector<DeferredChunk> deferred;
+    uint64_t deferred_total = 0;
 };
 
 namespace {
@@ -500,18 +506,24 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
 // Host path with dense output: worst-case slots stay on the device, compaction before D2H, so
 // only encoded bytes cross the bus.  Pipelined like run_host; the host learns a chunk's dense
 // size when its kernels are done, places the chunk behind the previous one and starts its copy.
+// deferred: the dense chunks stay in ctx->shard_dense (worst-case spacing) and only sizes, statuses
+// and details come back; run_host_dense_finish copies them out later.
 int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
                           const uint64_t* in_off, uint64_t n, const uint8_t* code_size,
                           uint64_t align, uint8_t* out_dense, uint64_t out_cap, uint64_t* out_off,
-                          uint32_t* status, uint32_t* detail, uint64_t* needed) {
+                          uint32_t* status, uint32_t* detail, uint64_t* needed, bool deferred = false) {
     if (!ctx) return SLZW_RC_INVALID;
-    if (!params_ok(params) || !in_off || !out_off || !status || !detail || (n && !out_dense) ||
+    if (!params_ok(params) || !in_off || !out_off || !status || !detail || (n && !out_dense && !deferred) ||
         (n && in_off[n] > in_off[0] && !in)) {
         snprintf(ctx->err, sizeof ctx->err, "invalid arguments");
         return SLZW_RC_INVALID;
     }
     out_off[0] = 0;
     if (needed) *needed = 0;
+    if (deferred) {
+        ctx->deferred.clear();
+        ctx->deferred_total = 0;
+    }
     if (n == 0) return SLZW_RC_OK;
     HostCallGuard busy(ctx);
     if (!busy.ok) return SLZW_RC_INVALID;
@@ -526,6 +538,18 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     const uint8_t* in_alias = (ctx->zero_copy_in && !predict) ? device_alias(in) : nullptr;
     uint64_t hbase = 0;  // dense bytes placed so far
     bool overflow = false;
+    // deferred: device offsets of the chunks inside ctx->shard_dense (worst-case spacing)
+    std::vector<uint64_t> dev_off(chunks + 1, 0);
+    if (deferred) {
+        for (size_t k = 0; k < chunks; k++) {
+            uint64_t worst = 0;
+            for (uint64_t i = cb[k]; i < cb[k + 1]; i++)
+                worst += ((slzw_encode_bound(params, in_off[i + 1] - in_off[i]) + 15) & ~15ull) + align;
+            dev_off[k + 1] = dev_off[k] + ((worst + 255) & ~255ull);
+        }
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        CK(ctx->shard_dense.reserve(dev_off[chunks] + 256), "cudaMalloc(dense shard)");
+    }
 
     auto enqueue = [&](size_t k) -> int {
         HostSlot& hs = ctx->pipe[k % kPipe];
@@ -551,7 +575,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
             std::lock_guard<std::mutex> lock(ctx->mu);
             if (!in_alias) CK(hs.in.reserve(in_hi - in_lo + 16), "cudaMalloc(in)");
             CK(hs.out.reserve(slot_bytes + 16), "cudaMalloc(slots)");
-            CK(hs.dense.reserve(slot_bytes + align * m + 16), "cudaMalloc(dense)");
+            if (!deferred) CK(hs.dense.reserve(slot_bytes + align * m + 16), "cudaMalloc(dense)");
             CK(hs.in_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(in_off)");
             CK(hs.out_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(out_off)");
             CK(hs.dense_off.reserve(sizeof(uint64_t) * (m + 1)), "cudaMalloc(dense_off)");
@@ -584,7 +608,8 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         }
         int rc = run_device(ctx, params, &d, s, Op::Encode);
         if (rc != SLZW_RC_OK) return rc;
-        CK(compact_launch(d.out, d.out_off, d.out_len, m, align, (uint8_t*)hs.dense.p,
+        CK(compact_launch(d.out, d.out_off, d.out_len, m, align,
+                          deferred ? (uint8_t*)ctx->shard_dense.p + dev_off[k] : (uint8_t*)hs.dense.p,
                           (uint64_t*)hs.dense_off.p, ctx->num_sms, s), "compaction launch");
         ctx->launches += 2;
         // the chunk's dense offsets come back in the out_len area of the stage (m + 1 entries)
@@ -605,10 +630,14 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         for (uint64_t i = 1; i <= m; i++) out_off[s0 + i] = hbase + st.out_len[i];
         memcpy(status + s0, st.status, sizeof(uint32_t) * m);
         memcpy(detail + s0, st.detail, sizeof(uint32_t) * m);
-        if (hbase + total > out_cap) overflow = true;
-        if (!overflow && total)
-            CK(cudaMemcpyAsync(out_dense + hbase, hs.dense.p, total, cudaMemcpyDeviceToHost, hs.stream),
-               "D2H dense");
+        if (deferred) {
+            ctx->deferred.push_back({dev_off[k], total});
+        } else {
+            if (hbase + total > out_cap) overflow = true;
+            if (!overflow && total)
+                CK(cudaMemcpyAsync(out_dense + hbase, hs.dense.p, total, cudaMemcpyDeviceToHost, hs.stream),
+                   "D2H dense");
+        }
         hbase += total;
         return SLZW_RC_OK;
     };
@@ -624,11 +653,40 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     if ((rc = place(chunks - 1)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
     for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->pipe[i].stream), "cudaStreamSynchronize");
     if (needed) *needed = hbase;
+    if (deferred) ctx->deferred_total = hbase;
     if (overflow) {
         snprintf(ctx->err, sizeof ctx->err, "dense output needs %llu bytes, capacity is %llu",
                  (unsigned long long)hbase, (unsigned long long)out_cap);
         return SLZW_RC_NOMEM;
     }
+    return SLZW_RC_OK;
+}
+
+// Second phase of the two-phase dense encode: the chunks that run_host_encode_dense(deferred) left
+// on the device go to dst back to back, the copies spread over the pipeline's streams.
+int run_host_dense_finish(slzw_ctx* ctx, uint8_t* dst, uint64_t cap) {
+    if (!ctx) return SLZW_RC_INVALID;
+    HostCallGuard busy(ctx);
+    if (!busy.ok) return SLZW_RC_INVALID;
+    if (ctx->deferred_total > cap || (ctx->deferred_total && !dst)) {
+        snprintf(ctx->err, sizeof ctx->err, "dense output needs %llu bytes, capacity is %llu",
+                 (unsigned long long)ctx->deferred_total, (unsigned long long)cap);
+        return SLZW_RC_NOMEM;
+    }
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
+    uint64_t at = 0;
+    for (size_t k = 0; k < ctx->deferred.size(); k++) {
+        const auto& c = ctx->deferred[k];
+        if (c.bytes)
+            CK(cudaMemcpyAsync(dst + at, (const uint8_t*)ctx->shard_dense.p + c.dev_off, c.bytes,
+                               cudaMemcpyDeviceToHost, ctx->pipe[k % kPipe].stream),
+               "D2H dense shard");
+        at += c.bytes;
+    }
+    for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->pipe[i].stream), "cudaStreamSynchronize");
+    ctx->deferred.clear();
+    ctx->deferred_total = 0;
     return SLZW_RC_OK;
 }
 
@@ -716,6 +774,7 @@ void slzw_destroy(slzw_ctx* ctx) {
             if (w.done) cudaEventDestroy(w.done);
         }
         for (int i = 0; i < kPipe; i++) ctx->pipe[i].release();
+        ctx->shard_dense.release();
     }
     delete ctx;
 }
@@ -785,6 +844,18 @@ int slzw_encode_batch_host_dense(slzw_ctx* ctx, const slzw_params* params, const
                                  uint64_t* needed) {
     return run_host_encode_dense(ctx, params, in, in_off, n, code_size, align, out_dense, out_cap,
                                  out_off, status, detail, needed);
+}
+
+int slzw_encode_batch_host_dense_begin(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
+                                       const uint64_t* in_off, uint64_t n, const uint8_t* code_size,
+                                       uint64_t align, uint64_t* out_off, uint32_t* status,
+                                       uint32_t* detail, uint64_t* total) {
+    return run_host_encode_dense(ctx, params, in, in_off, n, code_size, align, nullptr, ~0ull, out_off,
+                                 status, detail, total, true);
+}
+
+int slzw_encode_batch_host_dense_finish(slzw_ctx* ctx, uint8_t* out_dense, uint64_t out_cap) {
+    return run_host_dense_finish(ctx, out_dense, out_cap);
 }
 
 int slzw_encode(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in, uint64_t n,

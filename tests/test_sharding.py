@@ -28,6 +28,21 @@ def test_partition_covers_every_stream_once():
                 assert max(sizes) - min(sizes) <= 2 * int(lens.max()), "ranges are byte-balanced"
 
 
+def test_c_abi_partition_matches_the_host_model():
+    """slzw_partition_streams (what slzw_multi_* shards with; pure host code, runs without a GPU)
+    against sharding.partition."""
+    import lzw_b200
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 2, 7, 100, 1000, 5000):
+        lens = rng.integers(0, 70000, size=n)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lens)
+        off += np.uint64(12345)  # absolute offsets need not start at 0
+        for world in (1, 2, 3, 4, 8):
+            assert np.array_equal(lzw_b200.partition_streams(off, world).astype(np.int64),
+                                  sharding.partition(off, world)), (n, world)
+
+
 def test_shard_views_are_rebased():
     buf, off = T.make_batch(11, 40, 255)
     pieces = []
