@@ -1,20 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- the headline benchmark: batched TIFF-style LZW encode + decode (BASELINE config 3).
+"""bench.py -- batched LZW encode + decode on B200 (BASELINE.json configs 3, 4 and 5).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--streams S]
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+                    [--workload config3|config4|config5|readme] [--scaling weak|strong]
+                    [--endian le|be] [--streams S] [--single-process]
 
-One *step* = one pass of the hot path over one batch of synthetic TIFF strips: encode every
-strip, compact the compressed strips into a dense buffer (prefix sum + gather), decode them
-back.  `value` = uncompressed bytes of the batch / step time (so both directions are paid for
-every counted byte), inputs resident in HBM.  `e2e` = the same step through the host-buffer C
-ABI (slzw_{encode,decode}_batch_host) with pinned host memory, copies inside the timed region.
+The default line is the contract's: config 3 (65,536 synthetic TIFF strips PER GPU, weak scaling).
+`--workload config4` (4,096 GIF frames of 1 MiB, code sizes 2-8) and `--workload config5` (131,072
+chunks of 64 KiB of lorem-like text, fixed 12-bit codes, `--endian le|be`) default to STRONG
+scaling (the batch BASELINE.json names, sharded over the ranks by bytes); `--scaling` overrides.
 
-N > 1: one process per GPU (torchrun), every rank owns its own batch of the same shape (weak
-scaling, no data-path collective: streams are independent); time = max over ranks.
+One *step* = one pass of the hot path over the rank's batch: encode every stream, compact the
+encoded streams into a dense buffer (prefix sum + gather), decode them back.  `value` =
+uncompressed bytes of the whole job / step time (both directions are paid for every counted
+byte), inputs resident in HBM.  `e2e` = the same step through the host-buffer C ABI
+(slzw_encode_batch_host_dense + slzw_decode_batch_host) with pinned host memory, copies inside
+the timed region.  `--single-process`: ONE process drives all N GPUs through slzw_multi_* (one
+call per direction for the whole batch); only the end-to-end figure exists in that mode.
+
+N > 1: one process per GPU (torchrun), no data-path collective (streams are independent);
+time = max over ranks.  `--impl reference`: the reference's CPU algorithm (oracle/slzw_oracle.c,
+the C restatement of salzweg -- the Rust crate cannot be built in this image) on all host
+threads, on exactly the streams rank 0 of the GPU arm processes.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -30,6 +42,8 @@ if ROOT not in sys.path:
 
 METRIC = "uncompressed GB/s encode & decode, batched GIF/TIFF streams"
 UNIT = "GB/s"
+DEFAULT_STREAMS = {"config3": 65536, "config4": 4096, "config5": 131072}
+DEFAULT_SCALING = {"config3": "weak", "config4": "strong", "config5": "strong"}
 
 
 def parse_args():
@@ -38,23 +52,84 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=65536, help="TIFF strips per GPU (config 3: 65,536)")
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="strips in the CPU-baseline sample")
+    ap.add_argument("--workload", default="config3", choices=["config3", "config4", "config5", "readme"],
+                    help="config3: the bench line of the contract; config4 / config5: the other multi-GPU configs of "
+                         "BASELINE.json; readme: the rows of the reference's README (extra lines, not the contract's)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="weak: --streams per GPU; strong: --streams in total, sharded by bytes "
+                         "(default: weak for config3, strong for config4 / config5)")
+    ap.add_argument("--streams", type=int, default=None,
+                    help="streams (config3: 65,536 strips; config4: 4,096 frames; config5: 131,072 chunks)")
+    ap.add_argument("--endian", default="le", choices=["le", "be"], help="config5: bit order of the 12-bit codes")
+    ap.add_argument("--cpu-sample-mb", type=int, default=256, help="uncompressed MB in the CPU-baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config3", choices=["config3", "readme"],
-                    help="config3: the bench line of the contract; readme: the rows of the reference's README "
-                         "(tokyo image / lorem text, variable and fixed codes) -- extra lines, not the contract's")
-    return ap.parse_args()
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process, all --gpus devices through slzw_multi_* (end-to-end figure only)")
+    args = ap.parse_args()
+    if args.workload != "readme":
+        args.streams = args.streams or DEFAULT_STREAMS[args.workload]
+        args.scaling = args.scaling or DEFAULT_SCALING[args.workload]
+    return args
 
 
-def workload_config(args, n_streams, total_bytes):
+# ---- workloads --------------------------------------------------------------------------------------
+class Workload:
+    """The streams one rank processes: buf/off (+ per-stream code sizes), GPU and oracle params."""
+
+
+def make_workload(args, rank: int, world: int) -> Workload:
+    from lzw_b200 import workloads as W
+    from lzw_b200.types import Endianness, fixed_params, gif_params, tiff_params
+    from oracle import oracle as O  # parameter structs of the checker / CPU arm only
+
+    w = Workload()
+    w.cs = None
+    total_streams = args.streams * (world if args.scaling == "weak" else 1)
+    if args.scaling == "weak":
+        first, n = rank * args.streams, args.streams
+    else:
+        # strong: contiguous ranges of the one batch, balanced by bytes (slzw_partition_streams)
+        import lzw_b200
+        if args.workload == "config3":
+            lens = np.empty(total_streams, dtype=np.uint64)
+            W._wl().wl_tiff_strip_lens(W.SEED + 3, 0, total_streams, 8192, 57345, lens.ctypes.data)
+        else:
+            lens = np.full(total_streams, (1 << 20) if args.workload == "config4" else 65536, dtype=np.uint64)
+        off_all = np.zeros(total_streams + 1, dtype=np.uint64)
+        off_all[1:] = np.cumsum(lens)
+        b = lzw_b200.partition_streams(off_all, world)
+        first, n = int(b[rank]), int(b[rank + 1] - b[rank])
+    if args.workload == "config3":
+        w.buf, w.off = W.tiff_strips(n, first=first)
+        w.params, w.oparams = tiff_params(), O.tiff()
+        w.desc = ("config 3: synthetic TIFF strips, 8-64 KB, 4 entropy classes (random / photo walk / runs / Zipf "
+                  "text), TIFF-style LZW (MSB-first, early change)")
+    elif args.workload == "config4":
+        w.buf, w.off, w.cs = W.gif_frames(n, first=first)
+        w.params, w.oparams = gif_params(8), O.gif(8)
+        w.desc = ("config 4: synthetic 1024x1024 8-bit-palette GIF frames, code size 2-8 per frame (runs + dither, "
+                  "every 8th frame noise), GIF-style LZW (LSB-first)")
+    else:
+        big = args.endian == "be"
+        w.buf, w.off = W.text_chunks(n, first=first)
+        w.params = fixed_params(Endianness.BigEndian if big else Endianness.LittleEndian)
+        w.oparams = O.fixed(big)
+        w.desc = (f"config 5: synthetic lorem-like text in 64 KiB chunks, fixed 12-bit codes, "
+                  f"{'MSB' if big else 'LSB'}-first")
+    w.first, w.n, w.total_streams = first, n, total_streams
+    return w
+
+
+def workload_config(args, w: Workload, world: int, job_bytes: int):
     return {
-        "workload": f"config 3: {n_streams} synthetic TIFF strips per GPU, 8-64 KB, 4 entropy classes "
-                    "(random / photo walk / runs / Zipf text), TIFF-style LZW (MSB-first, early change)",
-        "streams_per_gpu": n_streams,
-        "uncompressed_bytes_per_gpu": int(total_bytes),
+        "workload": w.desc,
+        "streams_total": int(w.total_streams),
+        "streams_per_gpu": int(args.streams) if args.scaling == "weak" else None,
+        "uncompressed_bytes_total": int(job_bytes),
+        "scaling": args.scaling,
         "step": "encode + compact + decode of the whole batch",
+        "generator": "SplitMix64, one sub-seed per stream (tools/wlgen/wlgen.c), seed 0x5A172E60 + config number",
         "l2": "inputs larger than L2 (no explicit flush)",
         "sharding": "streams sharded by rank, no collective",
     }
@@ -114,13 +189,25 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_traffic(kernel: str, n_streams: int):
+def kernel_source_hash() -> str:
+    """Identifies the kernels a committed ncu capture belongs to."""
+    h = hashlib.sha256()
+    for name in ("encode_kernels.cu", "decode_kernels.cu", "slzw_device.cuh"):
+        with open(os.path.join(ROOT, "lzw_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(kernel: str, workload: str, n_streams: int):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel`, from the committed
-    `ncu --set full` capture of this same workload (profiles/r01_traffic.json), or None."""
+    `ncu --set full` capture of this same workload (profiles/r02_traffic.json).  None when there is
+    no capture of this workload / stream count, or when the kernel sources changed since."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f)
-        e = t.get(kernel)
+        if t.get("kernel_source_hash") != kernel_source_hash():
+            return None
+        e = t.get(workload, {}).get(kernel)
         if e and int(e.get("streams", -1)) == int(n_streams):
             return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"])
     except (OSError, ValueError, KeyError):
@@ -138,16 +225,19 @@ def measured_peak():
 
 
 # ---- CPU baseline / reference arm ---------------------------------------------------------------------
-def cpu_pass(buf, off, threads):
-    """One encode + decode pass of the oracle (restatement of salzweg) over a batch.
-    Returns (seconds_encode, seconds_decode)."""
+def cpu_pass(w: Workload, lo: int, hi: int, threads: int):
+    """One encode + decode pass of the oracle (restatement of salzweg) over streams [lo, hi) of the
+    workload.  Returns (seconds_encode, seconds_decode, uncompressed bytes)."""
     from lzw_b200 import workloads as W
     from oracle import oracle as O
+    off = (w.off[lo:hi + 1] - w.off[lo]).astype(np.uint64)
+    buf = w.buf[int(w.off[lo]):int(w.off[hi])]
+    cs = None if w.cs is None else w.cs[lo:hi]
     slots = W.encode_slots(off)
     t0 = time.perf_counter()
-    out, out_len, status, _ = O.encode_batch(O.tiff(), buf, off, slots, threads=threads)
+    out, out_len, status, _ = O.encode_batch(w.oparams, buf, off, slots, code_size=cs, threads=threads)
     t1 = time.perf_counter()
-    # dense copy of the encoded strips, untimed (the CPU path writes each strip where it wants)
+    # dense copy of the encoded streams, untimed (the CPU path writes each stream where it wants)
     dense_off = np.zeros(off.size, dtype=np.uint64)
     dense_off[1:] = np.cumsum(out_len)
     dense = np.empty(int(dense_off[-1]), dtype=np.uint8)
@@ -155,21 +245,22 @@ def cpu_pass(buf, off, threads):
         l = int(out_len[i])
         dense[int(dense_off[i]):int(dense_off[i]) + l] = out[int(slots[i]):int(slots[i]) + l]
     t2 = time.perf_counter()
-    O.decode_batch(O.tiff(), dense, dense_off, off, threads=threads)
+    O.decode_batch(w.oparams, dense, dense_off, off, code_size=cs, threads=threads)
     t3 = time.perf_counter()
-    return t1 - t0, t3 - t2
+    return t1 - t0, t3 - t2, int(off[-1])
 
 
-def cpu_baseline(buf, off, sample_streams, threads):
-    n = min(sample_streams, off.size - 1)
-    sub_off = off[: n + 1] - off[0]
-    sub = buf[int(off[0]):int(off[n])]
-    te, td = cpu_pass(sub, sub_off, threads)
-    nbytes = int(sub_off[-1])
+def streams_for_bytes(w: Workload, nbytes: int) -> int:
+    rel = w.off - w.off[0]
+    return int(max(1, min(w.n, np.searchsorted(rel, np.uint64(nbytes), side="right"))))
+
+
+def cpu_baseline(args, w: Workload, threads: int):
+    n = streams_for_bytes(w, args.cpu_sample_mb << 20)
+    te, td, nbytes = cpu_pass(w, 0, n, threads)
     # single-threaded figure on a smaller sample (the north star asks for both)
-    m = min(256, n)
-    t1e, t1d = cpu_pass(buf[int(off[0]):int(off[m])], off[: m + 1] - off[0], 1)
-    b1 = int(off[m] - off[0])
+    m = streams_for_bytes(w, 24 << 20)
+    t1e, t1d, b1 = cpu_pass(w, 0, m, 1)
     return {
         "value": nbytes / (te + td) / 1e9,
         "unit": UNIT,
@@ -177,7 +268,7 @@ def cpu_baseline(buf, off, sample_streams, threads):
         "single_thread": {"value": b1 / (t1e + t1d) / 1e9, "encode_gbs": b1 / t1e / 1e9,
                           "decode_gbs": b1 / t1d / 1e9, "sample_streams": m},
         "kind": "port",
-        "sample": f"first {n} strips of the workload ({nbytes} uncompressed bytes), oracle/slzw_oracle.c "
+        "sample": f"first {n} streams of the workload ({nbytes} uncompressed bytes), oracle/slzw_oracle.c "
                   f"(C restatement of salzweg; the Rust crate cannot be built here), one stream per task "
                   f"over {threads} host threads",
         "encode_gbs": nbytes / te / 1e9,
@@ -186,32 +277,38 @@ def cpu_baseline(buf, off, sample_streams, threads):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores, on exactly
+    the streams rank 0 of the GPU arm processes (for N = 1: the whole job)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    from lzw_b200 import workloads as W
     threads = os.cpu_count() or 1
-    n = min(args.cpu_sample, args.streams)
-    buf, off = W.tiff_strips(n)
-    nbytes = int(off[-1])
+    w = make_workload(args, 0, world)
+    nbytes = int(w.off[-1])
+    job_bytes = nbytes * world if args.scaling == "weak" else None
     for _ in range(args.warmup):
-        cpu_pass(buf, off, threads)
+        cpu_pass(w, 0, w.n, threads)
     te = td = 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        a, b = cpu_pass(buf, off, threads)
+        a, b, _ = cpu_pass(w, 0, w.n, threads)
         te += a
         td += b
     wall = time.perf_counter() - t0
     value = nbytes * args.steps / (te + td) / 1e9
-    sample = (f"{n} strips ({nbytes} uncompressed bytes) of config 3 per step, oracle/slzw_oracle.c "
-              f"(C restatement of salzweg; no Rust toolchain to build the crate), {threads} host threads")
+    sample = (f"the {w.n} streams of rank 0 ({nbytes} uncompressed bytes) per step"
+              + ("" if world == 1 else f" -- one rank's share of the {world}-GPU job, the CPU arm is a rate")
+              + f", oracle/slzw_oracle.c (C restatement of salzweg; no Rust toolchain to build the crate), "
+                f"{threads} host threads")
+    cfg = workload_config(args, w, world, job_bytes if job_bytes is not None else nbytes)
+    if args.scaling == "strong" and world > 1:
+        cfg["uncompressed_bytes_total"] = None  # only rank 0's shard is generated here
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": (te + td) / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic", "config": workload_config(args, n, nbytes),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "encode_gbs": nbytes * args.steps / te / 1e9,
                          "decode_gbs": nbytes * args.steps / td / 1e9},
@@ -246,14 +343,39 @@ def bind_to_gpu_numa_node(index: int):
     return None
 
 
+def host_link_probe(dev, nbytes: int = 1 << 30):
+    """Pinned H2D and D2H copies of `nbytes` each, running at the same time on two streams: what
+    the host side of this process can move per direction while the other direction is busy (the
+    ceiling of any host-buffer path; tools/e2e_probe.py measures several processes at once)."""
+    import torch
+    try:
+        h_a = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        h_b = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    except RuntimeError:
+        return None
+    d_a = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_b = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    best = None
+    for _ in range(3):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return nbytes / best / 1e9  # per direction, both directions busy
+
+
 # ---- our arm ---------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import lzw_b200
-    from lzw_b200 import workloads as W
-    from lzw_b200.types import tiff_params
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -267,11 +389,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     codec = lzw_b200.Codec(local_rank)
-    params = tiff_params()
-
-    # ---- synthetic batch of this rank (weak scaling: same shape, different seed per rank) ----
-    buf, off = W.tiff_strips(args.streams, seed=W.SEED + 3 + 1000 * rank)
-    n = off.size - 1
+    from lzw_b200 import workloads as W
+    w = make_workload(args, rank, world)
+    params, buf, off, n = w.params, w.buf, w.off, w.n
     total = int(off[-1])
     slots = W.encode_slots(off)
 
@@ -281,6 +401,8 @@ def run_ours(args):
     t_in = torch.from_numpy(buf).to(dev)
     t_off = i64(off)
     t_slots = i64(slots)
+    t_cs = torch.from_numpy(w.cs).to(dev) if w.cs is not None else None
+    cs_ptr = t_cs.data_ptr() if t_cs is not None else 0
     t_enc = torch.empty(int(slots[-1]), dtype=torch.uint8, device=dev)
     t_enc_len = torch.zeros(n, dtype=torch.int64, device=dev)
     t_enc_st = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -300,7 +422,7 @@ def run_ours(args):
             ev[0].record(stream)
         codec.encode_batch_device(params, n, t_in.data_ptr(), t_off.data_ptr(), t_enc.data_ptr(),
                                   t_slots.data_ptr(), t_enc_len.data_ptr(), t_enc_st.data_ptr(),
-                                  t_enc_det.data_ptr(), stream=sp)
+                                  t_enc_det.data_ptr(), code_size_ptr=cs_ptr, stream=sp)
         if ev:
             ev[1].record(stream)
         codec.compact_device(t_enc.data_ptr(), t_slots.data_ptr(), t_enc_len.data_ptr(), n,
@@ -309,7 +431,7 @@ def run_ours(args):
             ev[2].record(stream)
         codec.decode_batch_device(params, n, t_dense.data_ptr(), t_dense_off.data_ptr(), t_dec.data_ptr(),
                                   t_off.data_ptr(), t_dec_len.data_ptr(), t_dec_st.data_ptr(),
-                                  t_dec_det.data_ptr(), stream=sp)
+                                  t_dec_det.data_ptr(), code_size_ptr=cs_ptr, stream=sp)
         if ev:
             ev[3].record(stream)
 
@@ -358,33 +480,45 @@ def run_ours(args):
         "compressed_bytes": comp_total,
         "streams_deferred_to_exact_decoder": int(codec.last_deferred().size),
     }
-    # oracle check of a sample (bytes, sizes, statuses), rank 0 only
-    if rank == 0:
-        from oracle import oracle as O
-        m = min(512, n)
-        o_out, o_len, o_st, _ = O.encode_batch(O.tiff(), buf[: int(off[m])], off[: m + 1], slots[: m + 1],
-                                               threads=os.cpu_count() or 1)
-        g_len = t_enc_len[:m].cpu().numpy().astype(np.uint64)
-        g_out = t_enc[: int(slots[m])].cpu().numpy()
-        same = bool(np.array_equal(g_len, o_len)) and all(
-            np.array_equal(g_out[int(slots[i]):int(slots[i]) + int(o_len[i])],
-                           o_out[int(slots[i]):int(slots[i]) + int(o_len[i])]) for i in range(m))
-        parity["oracle_sample_streams"] = m
-        parity["oracle_sample_byte_exact"] = same
+    # oracle check of a sample (bytes, sizes, statuses) on every rank's first streams, gathered on rank 0
+    from oracle import oracle as O
+    m = streams_for_bytes(w, 24 << 20)
+    o_out, o_len, o_st, _ = O.encode_batch(w.oparams, buf[: int(off[m])], off[: m + 1], slots[: m + 1],
+                                           code_size=None if w.cs is None else w.cs[:m],
+                                           threads=max(1, (os.cpu_count() or 1) // world))
+    g_len = t_enc_len[:m].cpu().numpy().astype(np.uint64)
+    g_out = t_enc[: int(slots[m])].cpu().numpy()
+    same = bool(np.array_equal(g_len, o_len)) and bool(np.array_equal(enc_st[:m], o_st)) and all(
+        np.array_equal(g_out[int(slots[i]):int(slots[i]) + int(o_len[i])],
+                       o_out[int(slots[i]):int(slots[i]) + int(o_len[i])]) for i in range(m))
+    parity["oracle_sample_streams"] = m
+    parity["oracle_sample_byte_exact"] = same
 
-    # ---- max over ranks ----
+    # ---- max over ranks; whole-job totals ----
     t = torch.tensor([elapsed_ms, enc_ms, cmp_ms, dec_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(total), float(comp_total), float(n), float(same), float(round_trip_bytes_ok)],
+                       dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allt = [torch.zeros_like(tot) for _ in range(world)]
+        dist.all_gather(allt, tot)
+    else:
+        allt = [tot]
     elapsed_ms, enc_ms, cmp_ms, dec_ms = [float(x) for x in t.tolist()]
+    job_bytes = int(sum(float(x[0]) for x in allt))
+    job_comp = int(sum(float(x[1]) for x in allt))
+    parity["all_ranks_oracle_sample_byte_exact"] = all(bool(x[3]) for x in allt)
+    parity["all_ranks_round_trip_bytes_equal"] = all(bool(x[4]) for x in allt)
     ms_per_step = elapsed_ms / args.steps
-    value = world * total / (ms_per_step * 1e-3) / 1e9
+    value = job_bytes / (ms_per_step * 1e-3) / 1e9
 
     # ---- end to end through the host-buffer C ABI (pinned host memory) ----
     e2e = None
     if not args.no_e2e:
         # device memory of the kernel-only measurement is no longer needed
         del t_in, t_enc, t_dense, t_dec
+        torch.cuda.empty_cache()
+        link = host_link_probe(dev)
         torch.cuda.empty_cache()
         dense_cap = comp_total + comp_total // 64 + (1 << 20)  # the compressed size is known by now
         pinned = True
@@ -396,68 +530,162 @@ def run_ours(args):
             pinned = False
             h_in, h_dense, h_dec = buf, np.empty(dense_cap, dtype=np.uint8), np.empty(total, dtype=np.uint8)
         e2e_steps = max(1, min(args.steps, 3))
-        h2d = d2h = 0
-        # one untimed pass: staging buffers of the host path are allocated on first use
-        dense, doff, st, det = codec.encode_batch_dense(params, h_in, off, out=h_dense)
-        codec.decode_batch(params, dense, doff, off, out=h_dec)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            dense, doff, st, det = codec.encode_batch_dense(params, h_in, off, out=h_dense)
-            dec, dlen, dst, ddet = codec.decode_batch(params, dense, doff, off, out=h_dec)
-            h2d += total + dense.size + 3 * 8 * (n + 1)
-            d2h += dense.size + total + 8 * (n + 1) + 8 * n + 4 * 4 * n
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dt = float(te.item())
-        e2e = {"value": world * total * e2e_steps / dt / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
+
+        def e2e_pass(hi, hd, ho):
+            dense, doff, st, det = codec.encode_batch_dense(params, hi, off, code_size=w.cs, out=hd)
+            dec, dlen, dst, ddet = codec.decode_batch(params, dense, doff, off, code_size=w.cs, out=ho)
+            return dense, dec
+
+        def timed(hi, hd, ho, steps):
+            e2e_pass(hi, hd, ho)  # untimed: staging buffers of the host path are allocated on first use
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                dense, dec = e2e_pass(hi, hd, ho)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            te = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            return float(te.item()), dense, dec
+
+        dt, dense, dec = timed(h_in, h_dense, h_dec, e2e_steps)
+        h2d = total + dense.size + 3 * 8 * (n + 1)
+        d2h = dense.size + total + 8 * (n + 1) + 8 * n + 4 * 4 * n
+        e2e = {"value": job_bytes * e2e_steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "steps": e2e_steps, "round_trip_ok": bool(np.array_equal(dec[:total], buf)), "pinned": pinned,
                "numa_node_rank0": numa_node,
+               "host_link_gbs_per_direction": link,
+               "frac_of_host_link": (max(h2d, d2h) * e2e_steps / dt / 1e9 / link) if link else None,
                "note": "slzw_encode_batch_host_dense + slzw_decode_batch_host on pinned host buffers; the "
                        "encoder reads its pinned input in place over PCIe (counted in h2d_bytes_per_step), "
-                       "everything else is cudaMemcpyAsync inside the call"}
+                       "everything else is cudaMemcpyAsync inside the call; host_link = pinned H2D and D2H "
+                       "copies of 1 GiB running at the same time from this process"}
+        if pinned and world == 1 and total <= (4 << 30):
+            # the same calls on pageable buffers (numpy arrays): every copy is staged by the driver
+            p_dense = np.empty(dense_cap, dtype=np.uint8)
+            p_dec = np.empty(total, dtype=np.uint8)
+            dtp, _, decp = timed(buf, p_dense, p_dec, 1)
+            e2e["pageable"] = {"value": job_bytes / dtp / 1e9, "unit": UNIT,
+                               "round_trip_ok": bool(np.array_equal(decp[:total], buf))}
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        comp = parity["compressed_bytes"]
+        # the roofline describes one launch on one GPU: this rank's bytes
         kernels = {
-            "encode": {"ms": enc_ms, "algorithmic_bytes": total + comp},
-            "compact": {"ms": cmp_ms, "algorithmic_bytes": 2 * comp},
+            "encode": {"ms": enc_ms, "algorithmic_bytes": total + comp_total},
+            "compact": {"ms": cmp_ms, "algorithmic_bytes": 2 * comp_total},
             # scheduler + fast kernel + exact kernel over the deferred streams
-            "decode": {"ms": dec_ms, "algorithmic_bytes": total + comp},
+            "decode": {"ms": dec_ms, "algorithmic_bytes": total + comp_total},
         }
         for k in kernels.values():
             k["achieved_gbs"] = k["algorithmic_bytes"] / (k["ms"] * 1e-3) / 1e9
             k["frac_of_peak"] = k["achieved_gbs"] / peak
         dom = max(("encode", "decode"), key=lambda k: kernels[k]["ms"])
+        wl_key = args.workload + ("_be" if args.workload == "config5" and args.endian == "be" else "")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, n, total),
-            "encode_gbs": world * total / (enc_ms * 1e-3) / 1e9,
-            "decode_gbs": world * total / (dec_ms * 1e-3) / 1e9,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, w, world, job_bytes),
+            "encode_gbs": job_bytes / (enc_ms * 1e-3) / 1e9,
+            "decode_gbs": job_bytes / (dec_ms * 1e-3) / 1e9,
+            "compression_ratio": job_bytes / max(job_comp, 1),
             "roofline": {"bound": "hbm", "kernel": f"slzw_{dom}_kernel", "achieved": kernels[dom]["achieved_gbs"],
                          "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": kernels[dom]["frac_of_peak"],
-                         "traffic": measured_traffic(f"slzw_{dom}_kernel", n),
+                         "traffic": measured_traffic(f"slzw_{dom}_kernel", wl_key, n),
+                         "traffic_source": "profiles/r02_traffic.json (ncu --set full of this workload; null when the "
+                                           "kernel sources changed since the capture)",
                          "algorithmic_bytes_per_launch": kernels[dom]["algorithmic_bytes"],
-                         "launch_ms": kernels[dom]["ms"], "frac_of_nominal_8000": kernels[dom]["achieved_gbs"] / 8000.0},
+                         "launch_ms": kernels[dom]["ms"], "frac_of_nominal_8000": kernels[dom]["achieved_gbs"] / 8000.0,
+                         "scope": "one launch on rank 0's GPU"},
             "kernels": kernels,
             "clocks": clocks, "gpu_launches": int(launches), "parity": parity,
         }
         if e2e:
             line["e2e"] = e2e
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(buf, off, args.cpu_sample, os.cpu_count() or 1)
+            line["cpu_baseline"] = cpu_baseline(args, w, os.cpu_count() or 1)
         print(json.dumps(line))
     codec.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_single_process(args):
+    """One process, N GPUs, one call per direction for the whole batch (slzw_multi_*).  End to end
+    only: host buffers in, host buffers out."""
+    import torch
+
+    import lzw_b200
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; lzw_b200 has no CPU path")
+    nd = min(args.gpus, torch.cuda.device_count())
+    world_like = nd if args.scaling == "weak" else 1
+    # the whole job is one host batch: weak scaling = N times the per-GPU stream count
+    a2 = argparse.Namespace(**vars(args))
+    a2.streams = args.streams * world_like
+    a2.scaling = "strong"
+    w = make_workload(a2, 0, 1)
+    total = int(w.off[-1])
+    mc = lzw_b200.MultiCodec(n_devices=nd)
+    lens = np.diff(w.off)
+    dense_cap = int((((lens + 3 + lens // 3838 + 1) * 12 + 7) // 8 + 1).sum())
+    try:
+        h_in = torch.from_numpy(w.buf).pin_memory().numpy()
+        h_dense = torch.empty(dense_cap, dtype=torch.uint8).pin_memory().numpy()
+        h_dec = torch.empty(total, dtype=torch.uint8).pin_memory().numpy()
+        pinned = True
+    except RuntimeError:
+        h_in, h_dense, h_dec, pinned = w.buf, np.empty(dense_cap, dtype=np.uint8), np.empty(total, dtype=np.uint8), False
+
+    def one():
+        dense, doff, st, det = mc.encode_batch_dense(w.params, h_in, w.off, code_size=w.cs, out=h_dense)
+        dec, dlen, dst, ddet = mc.decode_batch(w.params, dense, doff, w.off, code_size=w.cs, out=h_dec)
+        return dense, doff, st, dec, dst
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        one()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = mc.kernel_launches
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dense, doff, st, dec, dst = one()
+    for d in range(nd):
+        torch.cuda.synchronize(d)
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    # oracle sample
+    from lzw_b200 import workloads as W
+    from oracle import oracle as O
+    m = streams_for_bytes(w, 24 << 20)
+    sl = W.encode_slots(w.off[: m + 1])
+    o_out, o_len, o_st, _ = O.encode_batch(w.oparams, w.buf[: int(w.off[m])], w.off[: m + 1], sl,
+                                           code_size=None if w.cs is None else w.cs[:m], threads=os.cpu_count() or 1)
+    same = bool(np.array_equal(np.diff(doff)[:m], o_len)) and all(
+        np.array_equal(dense[int(doff[i]):int(doff[i + 1])], o_out[int(sl[i]):int(sl[i]) + int(o_len[i])])
+        for i in range(m))
+    value = total * steps / dt / 1e9
+    n = w.n
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nd, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "mode": "single process, slzw_multi_* (value IS the end-to-end figure)",
+        "config": workload_config(a2, w, 1, total),
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": total + int(dense.size) + 3 * 8 * (n + 1),
+                "d2h_bytes_per_step": int(dense.size) + total + 8 * (n + 1) + 8 * n + 16 * n, "pinned": pinned,
+                "round_trip_ok": bool(np.array_equal(dec[:total], w.buf)),
+                "note": "slzw_multi_encode_batch_host_dense + slzw_multi_decode_batch_host: one call per direction for "
+                        "the whole batch, sharded by bytes over the devices, sizes gathered on the host"},
+        "parity": {"oracle_sample_streams": m, "oracle_sample_byte_exact": same,
+                   "encode_status_ok": int((st == 0).sum()), "decode_status_ok": int((dst == 0).sum())},
+        "clocks": clocks, "gpu_launches": int(mc.kernel_launches - launches0),
+    }))
+    mc.close()
 
 
 # ---- the reference's own README rows (SURVEY 8f.4) ----------------------------------------------------
@@ -586,6 +814,8 @@ def main():
         return run_readme_rows(args)
     if args.impl == "reference":
         run_reference(args)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_ours(args)
 

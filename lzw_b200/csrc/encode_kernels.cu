@@ -360,6 +360,104 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
     m.ncodes = (cpa - cbase) >> 1;
 }
 
+// ---- latency variant of the match loop: few streams, long streams ---------------------------------
+// A batch with no more streams than the device has shared-memory dictionaries (config 4 sharded
+// over 8 GPUs: 512 frames of 1 MiB per GPU; a single-stream call) is bound by the dependent chain
+// of ONE stream, not by instruction issue.  The bucket lookups above pay a collective load, a warp
+// reduction and a ballot per byte (about 270 cycles per byte on a 1 MiB frame); here every lane
+// runs the same scalar chain and nothing crosses lanes: the dictionary is 512 buckets of 8 slots,
+// a lookup is two 128-bit shared-memory loads of one bucket (a broadcast: all lanes read the same
+// address), a min tree over slot ^ ~key (same complemented slots and q codes as above: the minimum
+// is below 4095 iff the bucket holds the key, and then it is the new prefix), and a full bucket
+// continues at bucket + step(byte) (odd step: double hashing over buckets, 1.18 buckets per byte
+// on the config-3 strips, tools/exp/probe_sim.c).  LDS -> 3 ALU levels -> compare -> branch.
+// rec[i] = {byte << 12 | q(byte), hash9(byte) << 5}; tb = shared address of the 16 KB table.
+template <bool FIXED>
+__device__ __forceinline__ void match_tile_lat(uint32_t* __restrict__ table, const uint32_t tb,
+                                               const uint2* __restrict__ rec, uint16_t* __restrict__ codes,
+                                               const int lane, const uint32_t len, MatchState& m,
+                                               const uint32_t cs, const uint32_t inc,
+                                               const uint32_t clear_code, const uint32_t first_code) {
+    constexpr uint32_t kMask8 = 0x3FE0u;  // byte offset of a 32-byte bucket
+    uint32_t q = m.t >> 20;
+    uint32_t ncs = m.ncs;
+    uint32_t ws = FIXED ? 12u : m.ws;
+    uint32_t mask = m.mask;
+    uint32_t until = m.until;
+    // codes carry a width tag only when a width change can happen inside this tile
+    uint32_t wtag = (!FIXED && until <= len) ? ws << 12 : 0u;
+    const uint32_t cbase = (uint32_t)__cvta_generic_to_shared(codes);
+    uint32_t cpa = cbase + 2u * m.ncodes;
+#pragma unroll 2
+    for (uint32_t i = 0; i < len; i++) {
+        const uint2 rc = rec[i];
+        const uint32_t nkey = ~((q << 20) | (rc.x & 0xFF000u));
+        uint32_t a = tb | (((q << 5) ^ rc.y) & kMask8);
+#pragma unroll 1
+        for (;;) {
+            uint4 e0, e1;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(e0.x), "=r"(e0.y), "=r"(e0.z), "=r"(e0.w) : "r"(a));
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(e1.x), "=r"(e1.y), "=r"(e1.z), "=r"(e1.w) : "r"(a + 16u));
+            const uint32_t m0 = min(min(e0.x ^ nkey, e0.y ^ nkey), e0.z ^ nkey);
+            const uint32_t m1 = min(min(e0.w ^ nkey, e1.x ^ nkey), e1.y ^ nkey);
+            const uint32_t m2 = min(e1.z ^ nkey, e1.w ^ nkey);
+            const uint32_t c = min(min(m0, m1), m2);
+            if (c < 4095u) {  // find_word hit, encoder.rs:319-320
+                q = c;
+                break;
+            }
+            if (e1.w != 0u) {  // full bucket without the key: it may have gone to the next one
+                const uint32_t stp = ((rc.x << 5) & kMask8) | 32u;
+                a = (a & ~kMask8) | ((a + stp) & kMask8);
+                continue;
+            }
+            // miss: encoder.rs:322-324 / 645-649
+            sts_u16(cpa, q | wtag);
+            cpa += 2u;
+            if (!FIXED || until != 0u) {
+                // first empty slot of the bucket (slots fill from 0 upwards); every lane stores the
+                // same word to the same address
+                const bool up = e0.w != 0u;
+                const uint32_t s0 = up ? e1.x : e0.x, s1 = up ? e1.y : e0.y, s2 = up ? e1.z : e0.z;
+                const bool t1 = s1 == 0u;
+                const uint32_t lo = t1 ? s0 : s2;
+                const uint32_t idx = (up ? 4u : 0u) + (t1 ? 0u : 2u) + (lo != 0u ? 1u : 0u);
+                tbl_st(a + 4u * idx, nkey & ~(ncs & 0xFFFu));
+                ncs += kScr;
+                until--;
+                if (!FIXED && until == 0u) {  // new index == mask, encoder.rs:326
+                    if (ws < 12u) {           // encoder.rs:327-328
+                        ws++;
+                        wtag = ws << 12;
+                        const uint32_t nm = (1u << ws) - inc;
+                        until = nm - mask;
+                        mask = nm;
+                    } else {                  // encoder.rs:329-333: clear at 12 bits, dictionary restarts
+                        sts_u16(cpa, scrq<true>(clear_code) | (12u << 12));
+                        cpa += 2u;
+                        ws = cs + 1u;
+                        wtag = ws << 12;
+                        mask = (1u << ws) - inc;
+                        until = mask - first_code + 1u;
+                        ncs = scrq<true>(first_code);
+                        __syncwarp();
+                        clear_table(table, lane);
+                        __syncwarp();
+                    }
+                }
+            }
+            q = rc.x & 0xFFFu;  // prefix = this byte
+            break;
+        }
+    }
+    m.t = q << 20;
+    m.ncs = ncs & 0xFFFu;
+    m.ws = ws;
+    m.mask = mask;
+    m.until = until;
+    m.ncodes = (cpa - cbase) >> 1;
+}
+
 // The 32-bit word of lane `lane` of the tile whose first byte is at `p` (skew = p & 3): the
 // aligned word at p - skew + 4 * lane, or 0 when it holds no byte of [p, p + tile_len).  A word
 // that lies partly outside the tile is assembled from byte loads, so nothing outside
@@ -382,7 +480,7 @@ __device__ __forceinline__ uint32_t load_tile_word(const uint8_t* __restrict__ p
 // unused); otherwise `table` / `tb` are the generic pointer and the shared-window address of its
 // 16 KB.  One function body for both kinds of warp: everything but the match loop is shared, which
 // keeps the instruction footprint of the 28 warps down.
-template <int TILE, bool FIXED, bool HAS_TMEM, int U>
+template <int TILE, bool FIXED, bool HAS_TMEM, int U, bool LAT = false>
 __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restrict__ table,
                               const uint32_t tb, const bool tmem_warp, EncMisc<TILE>& S, int lane) {
     const bool TMEM = HAS_TMEM && tmem_warp;
@@ -540,7 +638,8 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
                 const uint32_t h7 = ((k * kByteMul) >> 2) & 0x7Fu;
                 // bucket lookups: the low 12 bits carry q of the byte itself (the prefix after a miss)
                 rec[idx] = make_uint2((k << 12) | scrq<true>(k), TMEM ? (tb | h7)
-                                               : (h7 << 7));
+                                               : LAT ? (((k * kByteMul) << 5) & 0x3FE0u)
+                                                     : (h7 << 7));
                 if (!FIXED && k > max_code && idx < bad) bad = idx;
             }
         }
@@ -569,7 +668,9 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
 #define SLZW_MATCH_B(TM, MD)                                                                        \
     match_tile_bucket<FIXED, TM, (MD == 1 ? U : kU0), MD>(table, TM ? 0u : (tb | (4u * (uint32_t)lane)), TM ? tb : 0u, rec, \
                                         codes, lane, len, m, cs, inc, clear_code, first_code)
-            if (TMEM) {
+            if constexpr (LAT) {
+                match_tile_lat<FIXED>(table, tb, rec, codes, lane, len, m, cs, inc, clear_code, first_code);
+            } else if (TMEM) {
                 if (mode == 0) SLZW_MATCH_B(true, 0);
                 else if (mode == 1) SLZW_MATCH_B(true, 1);
                 else if constexpr (FIXED) SLZW_MATCH_B(true, 2);
@@ -666,7 +767,7 @@ struct EncLayout {
 
 // Warps [0, TWARPS) keep their dictionary in tensor memory, warps [TWARPS, TWARPS + SWARPS) in
 // shared memory.
-template <int TILE, int SWARPS, int TWARPS, int U, bool FIXED>
+template <int TILE, int SWARPS, int TWARPS, int U, bool FIXED, bool LAT = false>
 __global__ void __launch_bounds__((SWARPS + TWARPS) * kWarpSize, 1)
 slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -710,7 +811,7 @@ slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= a.n) break;
         const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-        encode_stream<TILE, FIXED, (TWARPS > 0), U>(a, sid, table, tb, tmem_warp, S, lane);
+        encode_stream<TILE, FIXED, (TWARPS > 0), U, LAT>(a, sid, table, tb, tmem_warp, S, lane);
     }
 
     if constexpr (TWARPS > 0) {
@@ -730,7 +831,8 @@ slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
 
 // ---- launch configuration ---------------------------------------------------------------------
 // {input tile, warps with a shared-memory dictionary, warps with a tensor-memory dictionary}
-template <int TILE, int SWARPS, int TWARPS, int U>
+// LAT (latency variant) exists for the fixed flavour only.
+template <int TILE, int SWARPS, int TWARPS, int U, bool LAT = false>
 struct EncConfig {
     using L = EncLayout<TILE, SWARPS, SWARPS + TWARPS>;
     // the shared window of a CTA starts with 1 KB reserved by the system; taking the larger of
@@ -740,10 +842,12 @@ struct EncConfig {
         return (a > b ? a : b) + L::kHead;
     }
     static cudaError_t configure() {
-        cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true>,
+        if constexpr (!LAT) {
+            cudaError_t e = cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false, LAT>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
+            if (e != cudaSuccess) return e;
+        }
+        return cudaFuncSetAttribute(slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true, LAT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
     }
     static cudaError_t launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
@@ -751,9 +855,9 @@ struct EncConfig {
         const uint64_t ctas = (a.n + WARPS - 1) / WARPS;
         const int grid = (int)(ctas < (uint64_t)num_sms ? ctas : (uint64_t)num_sms);
         if (a.p.flavour == SLZW_FLAVOUR_FIXED)
-            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
-        else
-            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, true, LAT><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
+        else if constexpr (!LAT)
+            slzw_encode_kernel<TILE, SWARPS, TWARPS, U, false, LAT><<<grid, WARPS * kWarpSize, smem(), stream>>>(a, smem());
         return cudaGetLastError();
     }
 };
@@ -767,18 +871,27 @@ struct EncConfig {
 // for batches with few streams; with the min-reduction lookups this one is faster there too
 // (config 4, 512 frames of 1 MiB: 148.7 against 171.9 ms), so every batch takes the same kernel.
 using Enc0 = EncConfig<96, 12, 16, 2>;
+// Latency variant (match_tile_lat): 12 warps per SM, shared-memory dictionaries only, for batches
+// that would leave most of Enc0's 28 warps per SM without a stream -- FIXED flavour only, where it
+// wins (1,776 text chunks of 64 KiB: 10.5 against 16.3 ms; once the table is full nothing but
+// lookups is left).  On the variable flavours it loses (1 MiB GIF frames: 175 against 148 ms, TIFF
+// strips: 11.1 against 8.9 ms: its miss path is longer), so they keep the bucket lookups whatever
+// the batch size (profiles/r02_encode_notes.md).
+using EncLat = EncConfig<128, 12, 0, 2, true>;
 
 #ifndef SLZW_LANE_CONFIGS
 #define SLZW_LANE_CONFIGS(X)  // experiment configurations (exp/encode_lanes_config.cuh) are not built in
 #endif
 static int g_enc_config = 0;
 
-// tuning experiments only (SLZW_ENC_CONFIG): the configurations of exp/ when they are built in
+// tests and tuning (SLZW_ENC_CONFIG): 1 / 2 force the latency (fixed flavour) / throughput variant
+// whatever the batch size; 10.. are the configurations of exp/ when they are built in
 void encode_select_config(int c) { g_enc_config = c; }
 
 cudaError_t encode_configure() {
     cudaError_t e = Enc0::configure();
     if (e != cudaSuccess) return e;
+    if ((e = EncLat::configure()) != cudaSuccess) return e;
 #define X(id, C) if ((e = C::configure()) != cudaSuccess) return e;
     SLZW_LANE_CONFIGS(X)
 #undef X
@@ -801,7 +914,14 @@ cudaError_t encode_launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
 #define X(id, C) case id: return C::launch(a, num_sms, stream);
         SLZW_LANE_CONFIGS(X)
 #undef X
-        default: return Enc0::launch(a, num_sms, stream);
+        case 1: return a.p.flavour == SLZW_FLAVOUR_FIXED ? EncLat::launch(a, num_sms, stream)
+                                                         : Enc0::launch(a, num_sms, stream);
+        case 2: return Enc0::launch(a, num_sms, stream);
+        // fixed flavour, no more streams than the latency variant has warps on the device: the
+        // batch is bound by the chain of its longest stream
+        default: return (a.p.flavour == SLZW_FLAVOUR_FIXED && a.n <= (uint64_t)num_sms * 12u)
+                            ? EncLat::launch(a, num_sms, stream)
+                            : Enc0::launch(a, num_sms, stream);
     }
 }
 

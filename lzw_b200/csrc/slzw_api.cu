@@ -140,6 +140,7 @@ struct slzw_ctx {
     // overlap (PCIe is full duplex)
     HostSlot pipe[kPipe];
     bool zero_copy_in = true;  // SLZW_HOST_ZERO_COPY=0 stages pinned input like pageable input
+    bool chunk_min_streams = true;  // off when SLZW_HOST_CHUNK_BYTES is set (tests force tiny chunks)
     uint64_t enc_chunk_bytes = kEncChunkBytes;
     uint64_t dec_chunk_bytes = kDecChunkBytes;
     // TIFF Predictor = 2 applied by the host entry points (0 = off), slzw_set_tiff_predictor
@@ -338,9 +339,14 @@ const uint8_t* device_alias(const void* p) {
 }
 
 // Splits streams [0, n) into chunks of roughly equal weight (weight[i+1] - weight[i] per stream).
-std::vector<uint64_t> chunk_bounds(const uint64_t* weight, uint64_t n, uint64_t chunk_bytes) {
+// A chunk also has to fill the device (min_streams = streams in flight on it): a chunk with fewer
+// streams takes as long as its longest stream whatever its size, so a batch of few long streams
+// (config 4: 1 MiB frames, 145 ms each) goes through in few chunks (3.2 -> 11 GB/s end to end).
+std::vector<uint64_t> chunk_bounds(const uint64_t* weight, uint64_t n, uint64_t chunk_bytes,
+                                   uint64_t min_streams) {
     const uint64_t total = weight[n] - weight[0];
     uint64_t chunks = total / chunk_bytes;
+    if (min_streams && chunks > n / min_streams) chunks = n / min_streams;
     if (chunks < 1) chunks = 1;
     if (chunks > kMaxChunks) chunks = kMaxChunks;
     if (chunks > n) chunks = n;
@@ -410,7 +416,8 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
     // chunk by the larger side of the stream (uncompressed bytes)
     const std::vector<uint64_t> cb =
         chunk_bounds(needs_out && op == Op::Decode ? b->out_off : b->in_off, n,
-                     op == Op::Encode ? ctx->enc_chunk_bytes : ctx->dec_chunk_bytes);
+                     op == Op::Encode ? ctx->enc_chunk_bytes : ctx->dec_chunk_bytes,
+                     ctx->chunk_min_streams ? (uint64_t)ctx->num_sms * (op == Op::Encode ? 28u : 32u) : 0u);
     const size_t chunks = cb.size() - 1;
     // encode: pinned input is read in place (the decoder's input is small and its access pattern
     // re-reads tiles, it stays staged)
@@ -531,7 +538,8 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     NvtxRange range("slzw encode batch, dense (host pipeline)");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
-    const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->enc_chunk_bytes);
+    const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->enc_chunk_bytes,
+                                                  ctx->chunk_min_streams ? (uint64_t)ctx->num_sms * 28u : 0u);
     const size_t chunks = cb.size() - 1;
     const bool predict = ctx->pred_row_bytes != 0;
     // pinned input is read in place, unless the predictor has to rewrite it on the device first
@@ -735,12 +743,18 @@ int slzw_create(int device, slzw_ctx** out) {
     if (!ctx) return SLZW_RC_NOMEM;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    if (const char* e = getenv("SLZW_ENC_CONFIG")) encode_select_config(atoi(e));  // tuning knob
+    {
+        const char* e = getenv("SLZW_ENC_CONFIG");  // tests / tuning knob, process-wide; unset = by batch size
+        encode_select_config(e ? atoi(e) : 0);
+    }
     if (const char* e = getenv("SLZW_DEC_CONFIG")) decode_select_config(atoi(e));  // tuning knob
     if (const char* e = getenv("SLZW_HOST_ZERO_COPY")) ctx->zero_copy_in = atoi(e) != 0;
     if (const char* e = getenv("SLZW_HOST_CHUNK_BYTES")) {
         const long long v = atoll(e);  // tests use tiny chunks
-        if (v > 0) ctx->enc_chunk_bytes = ctx->dec_chunk_bytes = (uint64_t)v;
+        if (v > 0) {
+            ctx->enc_chunk_bytes = ctx->dec_chunk_bytes = (uint64_t)v;
+            ctx->chunk_min_streams = false;
+        }
     }
     DeviceGuard guard(device);
     if (!guard.ok || encode_configure() != cudaSuccess || decode_exact_configure() != cudaSuccess ||

@@ -15,12 +15,27 @@ from tests import cases as T
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def codec():
+@pytest.fixture(scope="module", params=["default", "latency-variant"])
+def codec(request):
+    """Every test of this module runs twice: with the encoder the library picks by batch size, and
+    with the latency variant forced wherever it exists (fixed flavour; SLZW_ENC_CONFIG is read by
+    slzw_create).  The throughput kernel (tensor memory + ldmatrix buckets) handles every batch of
+    a variable flavour in both runs, whatever its size."""
+    import os
     import lzw_b200
+    old = os.environ.get("SLZW_ENC_CONFIG")
+    if request.param == "latency-variant":
+        os.environ["SLZW_ENC_CONFIG"] = "1"
+    else:
+        os.environ.pop("SLZW_ENC_CONFIG", None)
     c = lzw_b200.Codec(0)
     yield c
     c.close()
+    if old is None:
+        os.environ.pop("SLZW_ENC_CONFIG", None)
+    else:
+        os.environ["SLZW_ENC_CONFIG"] = old
+    lzw_b200.Codec(0).close()  # the setting is process-wide: back to what the environment says
 
 
 def gp(p):
@@ -558,3 +573,33 @@ def test_config5_fixed_text_chunks_full_size(codec):
         comp = _roundtrip_properties(codec, O.fixed(be), buf, off, oracle_streams=6)
         assert 0 < comp < buf.size
         assert len(codec.last_deferred()) == 0
+
+
+# ---- batches larger than one wave of the latency variant (12 streams per SM) ---------------------
+@pytest.mark.parametrize("p", [O.tiff(), O.gif(5), O.fixed(False), O.fixed(True)], ids=T.pname)
+def test_large_batch_with_error_streams(codec, p):
+    """More than 1,776 streams: the throughput kernel for every flavour (fixed included), with
+    rejected bytes, too-small slots and streams long enough to fill and freeze / reset the table."""
+    rng = np.random.default_rng(77)
+    n = 2000
+    hi = T.max_symbol(p)
+    streams = []
+    for i in range(n):
+        length = int(rng.choice([0, 1, 2, 40, 700, 2500, 7000], p=[.02, .02, .02, .2, .44, .2, .1]))
+        s = T.make_stream(rng, T.KINDS[i % len(T.KINDS)], length, hi)
+        if p.flavour == 0 and hi < 255 and i % 97 == 5 and s.size > 4:
+            s[int(rng.integers(0, s.size))] = hi + 1  # UnexpectedCode (or the unchecked first byte)
+        streams.append(s)
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([s.size for s in streams])
+    buf = np.concatenate(streams)
+    caps = [O.encode_bound(int(s.size)) if i % 53 else int(rng.integers(0, 30)) for i, s in enumerate(streams)]
+    slots = np.zeros(n + 1, dtype=np.uint64)
+    slots[1:] = np.cumsum(caps)
+    out, _, out_len, st, det = codec.encode_batch(gp(p), buf, off, out_off=slots)
+    o_out, o_len, o_st, o_det = O.encode_batch(p, buf, off, slots, threads=8)
+    assert np.array_equal(st, o_st) and np.array_equal(det, o_det) and np.array_equal(out_len, o_len)
+    assert int((o_st != 0).sum()) > 10
+    for i in range(n):
+        a, l = int(slots[i]), int(o_len[i])
+        assert np.array_equal(out[a:a + l], o_out[a:a + l]), f"stream {i}"

@@ -34,7 +34,7 @@ def main():
         params = gif_params(8)
     elif args.workload == "config5":
         buf, off = W.text_chunks(args.streams)
-        params = fixed_params(False)
+        params = fixed_params(lzw_b200.Endianness.LittleEndian)
     else:
         buf, off = W.tiff_strips(args.streams)
         params = tiff_params()
