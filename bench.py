@@ -343,7 +343,7 @@ def bind_to_gpu_numa_node(index: int):
     return None
 
 
-def host_link_probe(dev, nbytes: int = 1 << 30):
+def host_link_probe(dev, nbytes: int = 1 << 30, sync=None):
     """Pinned H2D and D2H copies of `nbytes` each, running at the same time on two streams: what
     the host side of this process can move per direction while the other direction is busy (the
     ceiling of any host-buffer path; tools/e2e_probe.py measures several processes at once)."""
@@ -359,6 +359,8 @@ def host_link_probe(dev, nbytes: int = 1 << 30):
     best = None
     for _ in range(3):
         torch.cuda.synchronize(dev)
+        if sync:
+            sync()  # all ranks copy at the same time: the ceiling the ranks' host paths share
         t0 = time.perf_counter()
         with torch.cuda.stream(s1):
             d_a.copy_(h_a, non_blocking=True)
@@ -518,7 +520,7 @@ def run_ours(args):
         # device memory of the kernel-only measurement is no longer needed
         del t_in, t_enc, t_dense, t_dec
         torch.cuda.empty_cache()
-        link = host_link_probe(dev)
+        link = host_link_probe(dev, sync=barrier)
         torch.cuda.empty_cache()
         dense_cap = comp_total + comp_total // 64 + (1 << 20)  # the compressed size is known by now
         pinned = True
@@ -561,7 +563,7 @@ def run_ours(args):
                "note": "slzw_encode_batch_host_dense + slzw_decode_batch_host on pinned host buffers; the "
                        "encoder reads its pinned input in place over PCIe (counted in h2d_bytes_per_step), "
                        "everything else is cudaMemcpyAsync inside the call; host_link = pinned H2D and D2H "
-                       "copies of 1 GiB running at the same time from this process"}
+                       "copies of 1 GiB running at the same time, on all ranks at once (this rank's share)"}
         if pinned and world == 1 and total <= (4 << 30):
             # the same calls on pageable buffers (numpy arrays): every copy is staged by the driver
             p_dense = np.empty(dense_cap, dtype=np.uint8)

@@ -321,6 +321,30 @@ __device__ __forceinline__ uint8_t ld_byte(const uint8_t* p) {
     return (uint8_t)v;
 }
 
+// Table accesses of the warps whose table lives in global memory: the 47 MB of tables are meant to
+// stay in L2 while 4.4 GB of input and output stream through it.  Without a hint the streaming
+// lines push table lines out, dirty: the round-1 capture at 65,536 strips shows 4.71 GB of DRAM
+// writes for 2.41 GB of output (profiles/r02_decode_65536_ncu_summary.txt).  An evict_last policy on
+// every table access keeps them (createpolicy + L2::cache_hint).
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t table_ld(const uint32_t* p, bool global_table, uint64_t pol) {
+    if (!global_table) return *p;
+    uint32_t v;
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;\n" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void table_st(uint32_t* p, uint32_t v, bool global_table, uint64_t pol) {
+    if (!global_table) {
+        *p = v;
+        return;
+    }
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;\n" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 constexpr int kFastWin = 1024;   // output bytes one step may produce (32 mask words)
 constexpr int kFastTile = 512;   // compressed bytes staged per tile
 constexpr uint32_t kLit = 0x80000000u;
@@ -341,7 +365,7 @@ struct FastWarpSmem {
 
 // Returns false when the stream has to be decoded by the exact kernel.
 __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, uint32_t* __restrict__ table,
-                                   FastWarpSmem& S, int lane) {
+                                   const bool global_table, const uint64_t pol, FastWarpSmem& S, int lane) {
     const uint64_t in_begin = a.in_off[sid];
     const uint64_t n = a.in_off[sid + 1] - in_begin;
     const uint8_t* src = a.in + in_begin;
@@ -471,7 +495,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, uint32_t* __
                 } else if (!hp && lane == 0) {
                     bad = true;  // first code is not a root: stale-table semantics, decoder.rs:230-236
                 } else if (c < nidx) {
-                    const uint32_t e = table[c];
+                    const uint32_t e = table_ld(table + c, global_table, pol);
                     len = e & 0xFFFu;
                     srci = seg_base + (e >> 12);
                 } else {  // c <= ni: an entry created inside this step, or the one being created
@@ -541,7 +565,7 @@ __device__ bool decode_stream_fast(const DevBatch& a, uint32_t sid, uint32_t* __
                 }
                 const uint32_t idx = nidx + (uint32_t)lane - adj;
                 if (act2 && (uint32_t)lane >= adj && idx < (uint32_t)kMaxTable)
-                    table[idx] = ((poff - seg_base) << 12) | ((plen + 1u) & 0xFFFu);
+                    table_st(table + idx, ((poff - seg_base) << 12) | ((plen + 1u) & 0xFFFu), global_table, pol);
             }
             // ---- copy ----
             if (dst) {
@@ -670,13 +694,15 @@ __global__ void __launch_bounds__((SW + GW) * kWarpSize, CTAS) slzw_decode_fast_
                                 : a.dec_tables + ((size_t)blockIdx.x * GW + (size_t)(warp - SW)) * kMaxTable;
     for (int i = lane; i < kFastWin / 32; i += kWarpSize) S.bits[i] = 0u;
     __syncwarp();
+    const bool global_table = warp >= SW;
+    const uint64_t pol = l2_keep_policy();
     for (;;) {
         unsigned long long q = 0;
         if (lane == 0) q = atomicAdd(a.queue, 1ull);
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= a.n) break;
         const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-        const bool done = decode_stream_fast(a, sid, table, S, lane);
+        const bool done = decode_stream_fast(a, sid, table, global_table, pol, S, lane);
         __syncwarp();
         if (!done) {
             // a deferred stream may have left word-start bits behind

@@ -37,6 +37,9 @@
 #ifndef SLZW_U0
 #define SLZW_U0 4
 #endif
+#ifndef SLZW_INSERT_SYNC
+#define SLZW_INSERT_SYNC 1  // __syncwarp() between a shared-memory insert and the next bucket load
+#endif
 #ifndef SLZW_HIT_REDUX
 #define SLZW_HIT_REDUX 1  // hit detection: one warp min-reduction (1) or ballot + find-first + shuffle (0)
 #endif
@@ -124,6 +127,15 @@ struct MatchState {
     uint32_t ncodes;  // codes buffered for the packer
 };
 
+// shared-memory address of this lane's row of bucket (prefix ^ hash7) & 127: one LOP3 + one IMAD
+// (written out because the compiler otherwise shifts first and masks afterwards: four instructions)
+__device__ __forceinline__ uint32_t bucket_row_addr(uint32_t row0, uint32_t prefix, uint32_t h7) {
+    uint32_t x, a;
+    asm("lop3.b32 %0, %1, %2, 0x7F, 0x28;\n" : "=r"(x) : "r"(prefix), "r"(h7));  // (prefix ^ h7) & 0x7F
+    asm("mad.lo.u32 %0, %1, 128, %2;\n" : "=r"(a) : "r"(x), "r"(row0));
+    return a;
+}
+
 // index of the most significant set bit (FLO)
 __device__ __forceinline__ uint32_t bfind(uint32_t v) {
     uint32_t r;
@@ -187,7 +199,7 @@ __device__ __forceinline__ void tmem_clear(uint32_t tbase) {
 // that owns the first empty slot inserts it); a full bucket overflows into the next one.  There is
 // no separate collision path and no speculation: 1.00 to 1.14 bucket loads per input byte on the
 // config-3 strips at the format's load factor of up to 0.94 (profiles/r01_encode_notes.md).
-// rec[i] = {byte << 12, hash7(byte) << 7} (shared memory) or {byte << 12, dictionary's
+// rec[i] = {byte << 12 | q(byte), hash7(byte)} (shared memory) or {byte << 12 | q(byte), dictionary's
 // tensor-memory address | hash7(byte)} (tensor memory); `tl` = shared address of this lane's slot
 // in bucket 0, `tb` = tensor-memory address of the dictionary.
 // MODE says what a miss may have to do in this tile (chosen per tile by the caller from the
@@ -207,7 +219,7 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                                                   const uint32_t clear_code,
                                                   const uint32_t first_code) {
     uint32_t t = m.t;                             // prefix' << 20: key position
-    uint32_t tp = TMEM ? m.t >> 20 : m.t >> 13;   // prefix' (column) / prefix' << 7 (bucket offset)
+    uint32_t tp = m.t >> 20;                      // prefix (q): its low 7 bits choose the bucket
     uint32_t ncs = m.ncs;                         // low 12 bits count, upper bits are garbage
     uint32_t ws = FIXED ? 12u : m.ws;
     uint32_t wtag = ws << 12;
@@ -230,7 +242,7 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
         /* slots hold ~(key | q): an empty slot is 0 and slot ^ ~key is q for the slot that   \
            holds the key, at least 4095 for every other one */                                   \
         const uint32_t key = ~(t | ((RC).x & 0xFF000u));                                        \
-        uint32_t a = TMEM ? ((tp & 0x7Fu) ^ (RC).y) : (tlr | ((tp ^ (RC).y) & kBucketMask));    \
+        uint32_t a = TMEM ? ((tp & 0x7Fu) ^ (RC).y) : bucket_row_addr(tlr, tp, (RC).y);         \
         /* Both bucket loads (tcgen05.ld, ldmatrix) are .sync.aligned: the warp is converged at   \
            every step, the compiler puts no divergence guard in front of the ballots and the     \
            shuffle, and the insert of the previous step (same warp, same memory pipe, program    \
@@ -249,7 +261,7 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                 const uint32_t c = __reduce_min_sync(kFullMask, v ^ key);                       \
                 if (c < 4095u) { /* find_word hit, encoder.rs:319-320 */                        \
                     t = c << 20;                                                                \
-                    tp = TMEM ? c : c << 7;                                                     \
+                    tp = c;                                                                     \
                     break;                                                                      \
                 }                                                                               \
             } else {                                                                            \
@@ -258,7 +270,7 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                 if (bal) {                                                                      \
                     const uint32_t c = __shfl_sync(kFullMask, x, (int)bfind(bal));              \
                     t = c << 20;                                                                \
-                    tp = TMEM ? c : c << 7;                                                     \
+                    tp = c;                                                                     \
                     break;                                                                      \
                 }                                                                               \
             }                                                                                   \
@@ -280,6 +292,9 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                     tmem_wait_st();                                                             \
                 } else {                                                                        \
                     if (mine) tbl_st(a ^ tlx, entry);                                           \
+                    /* the next ldmatrix reads this slot on behalf of another lane: order the   \
+                       store before it (memory model; measured cost: r02_encode_notes.md) */    \
+                    if (SLZW_INSERT_SYNC) __syncwarp();                                         \
                 }                                                                               \
                 ncs += kScr;                                                                    \
                 if (MODE == 1) {                                                                \
@@ -313,7 +328,7 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
             /* prefix = this byte: its q sits in the low bits of the record (only the low 7   \
                bits of tp / bits 7..13 of tp << 7 reach the bucket address) */                   \
             t = (RC).x << 20;                                                                   \
-            tp = TMEM ? ((RC).x & 0xFFFu) : (RC).x << 7;                                        \
+            tp = (RC).x & 0xFFFu;                                                               \
             break;                                                                              \
         }                                                                                       \
     }
@@ -639,7 +654,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
                 // bucket lookups: the low 12 bits carry q of the byte itself (the prefix after a miss)
                 rec[idx] = make_uint2((k << 12) | scrq<true>(k), TMEM ? (tb | h7)
                                                : LAT ? (((k * kByteMul) << 5) & 0x3FE0u)
-                                                     : (h7 << 7));
+                                                     : h7);
                 if (!FIXED && k > max_code && idx < bad) bad = idx;
             }
         }

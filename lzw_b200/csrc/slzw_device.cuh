@@ -57,37 +57,4 @@ __device__ __forceinline__ uint32_t stage_tile(const uint8_t* __restrict__ src, 
     return skew;
 }
 
-// Asynchronous tile staging: interior 16-byte chunks go global -> shared with cp.async
-// (LDGSTS, no register staging); ragged head/tail bytes are copied synchronously, so nothing
-// outside [src, src+len) is touched.  Commits one cp.async group.  Byte j lands at
-// tile[skew + j], skew = (address of src) & 15 is returned.
-__device__ __forceinline__ uint32_t stage_tile_async(const uint8_t* __restrict__ src, uint32_t len,
-                                                     uint8_t* tile, int lane) {
-    const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
-    const uint8_t* base = src - skew;
-    const uint32_t span = skew + len;
-    const uint32_t nchunks = (span + 15u) >> 4;
-    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
-    for (uint32_t c = lane; c < nchunks; c += kWarpSize) {
-        const uint32_t lo = c << 4;
-        if (lo >= skew && lo + 16u <= span) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(tile_s + lo),
-                         "l"(base + lo)
-                         : "memory");
-        } else {
-            for (uint32_t b = 0; b < 16u; b++) {
-                const uint32_t o = lo + b;
-                if (o >= skew && o < span) tile[o] = __ldg(base + o);
-            }
-        }
-    }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    return skew;
-}
-
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
 }  // namespace slzw

@@ -9,6 +9,6 @@ mkdir -p variants
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   $NVCC -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC,-fvisibility=hidden $flags -c -o variants/enc_$name.o encode_kernels.cu
-  $NVCC $ARCH -shared -o variants/libslzw_$name.so slzw_api.o variants/enc_$name.o decode_kernels.o sched_kernels.o predictor_kernels.o -cudart static
+  $NVCC $ARCH -shared -o variants/libslzw_$name.so slzw_api.o slzw_multi.o variants/enc_$name.o decode_kernels.o sched_kernels.o predictor_kernels.o -cudart static -lpthread
   echo built variants/libslzw_$name.so
 done
