@@ -443,6 +443,66 @@ inline std::vector<StreamResult> decode_batch(const uint8_t* data, const std::ve
                                 capacities.data(), code_sizes ? code_sizes->data() : nullptr);
 }
 
+// ---- the same batches over every GPU of the box (slzw_multi_*) -------------------------------------
+/// `salzweg::multi::encode_batch` / `decode_batch`: identical signatures and results; the batch is
+/// sharded by bytes over all visible sm_100 devices (one context and one worker thread each, no
+/// exchange between devices, sizes gathered on the host).  The device set is opened on first use.
+namespace multi {
+namespace detail {
+inline slzw_multi* box() {
+    static slzw_multi* m = [] {
+        slzw_multi* x = nullptr;
+        const int rc = slzw_multi_create(nullptr, 0, &x);
+        if (rc != SLZW_RC_OK)
+            throw std::runtime_error(rc == SLZW_RC_NO_DEVICE ? "salzweg: no sm_100 CUDA device (there is no CPU fallback)"
+                                                              : "salzweg: slzw_multi_create failed");
+        return x;
+    }();
+    return m;
+}
+[[noreturn]] inline void failure(const char* what) {
+    throw std::runtime_error(std::string("salzweg: ") + what + " failed: " + slzw_multi_last_error(box()));
+}
+}  // namespace detail
+
+inline int device_count() { return slzw_multi_device_count(detail::box()); }
+
+inline std::vector<StreamResult> encode_batch(const uint8_t* data, const std::vector<uint64_t>& offsets,
+                                              uint8_t flavour, uint8_t code_size, Endianness endianness,
+                                              CodeSizeStrategy strategy,
+                                              const std::vector<uint8_t>* code_sizes = nullptr) {
+    const uint64_t n = offsets.empty() ? 0 : offsets.size() - 1;
+    if (n == 0) return {};
+    const slzw_params p = salzweg::detail::params(flavour, code_size, endianness, strategy);
+    std::vector<uint64_t> out_off(n + 1, 0), len(n);
+    for (uint64_t i = 0; i < n; i++)
+        out_off[i + 1] = out_off[i] + ((slzw_encode_bound(&p, offsets[i + 1] - offsets[i]) + 15) & ~15ull);
+    std::vector<uint8_t> out(out_off[n] ? out_off[n] : 1);
+    std::vector<uint32_t> st(n), det(n);
+    slzw_batch b{data, offsets.data(), out.data(), out_off.data(), len.data(), st.data(), det.data(),
+                 code_sizes ? code_sizes->data() : nullptr, n};
+    if (slzw_multi_encode_batch_host(detail::box(), &p, &b) != SLZW_RC_OK) detail::failure("slzw_multi_encode_batch_host");
+    return salzweg::detail::collect(out, out_off, len, st, det);
+}
+
+inline std::vector<StreamResult> decode_batch(const uint8_t* data, const std::vector<uint64_t>& offsets,
+                                              const std::vector<uint64_t>& capacities, uint8_t flavour,
+                                              uint8_t code_size, Endianness endianness, CodeSizeStrategy strategy,
+                                              const std::vector<uint8_t>* code_sizes = nullptr) {
+    const uint64_t n = offsets.empty() ? 0 : offsets.size() - 1;
+    if (n == 0) return {};
+    const slzw_params p = salzweg::detail::params(flavour, code_size, endianness, strategy);
+    std::vector<uint64_t> out_off(n + 1, 0), len(n);
+    for (uint64_t i = 0; i < n; i++) out_off[i + 1] = out_off[i] + capacities[i];
+    std::vector<uint8_t> out(out_off[n] ? out_off[n] : 1);
+    std::vector<uint32_t> st(n), det(n);
+    slzw_batch b{data, offsets.data(), out.data(), out_off.data(), len.data(), st.data(), det.data(),
+                 code_sizes ? code_sizes->data() : nullptr, n};
+    if (slzw_multi_decode_batch_host(detail::box(), &p, &b) != SLZW_RC_OK) detail::failure("slzw_multi_decode_batch_host");
+    return salzweg::detail::collect(out, out_off, len, st, det);
+}
+}  // namespace multi
+
 // ---- coalescing of one-stream calls -------------------------------------------------
 namespace coalesced {
 

@@ -139,7 +139,11 @@ struct slzw_ctx {
     // chunk of streams, the kernels of the previous chunk and the D2H copy of the one before
     // overlap (PCIe is full duplex)
     HostSlot pipe[kPipe];
-    bool zero_copy_in = true;  // SLZW_HOST_ZERO_COPY=0 stages pinned input like pageable input
+    // pinned encoder input read in place by the kernels instead of staged (SLZW_HOST_ZERO_COPY): 0
+    // never; 1 (default) the first chunk of a call only -- the one chunk whose staging copy nothing
+    // hides; the kernels read host memory at 23 GB/s, the copy engine stages it at 55 GB/s
+    // (profiles/r02_e2e_notes.md); 2 every chunk
+    int zero_copy_in = 1;
     bool chunk_min_streams = true;  // off when SLZW_HOST_CHUNK_BYTES is set (tests force tiny chunks)
     uint64_t enc_chunk_bytes = kEncChunkBytes;
     uint64_t dec_chunk_bytes = kDecChunkBytes;
@@ -342,19 +346,51 @@ const uint8_t* device_alias(const void* p) {
 // A chunk also has to fill the device (min_streams = streams in flight on it): a chunk with fewer
 // streams takes as long as its longest stream whatever its size, so a batch of few long streams
 // (config 4: 1 MiB frames, 145 ms each) goes through in few chunks (3.2 -> 11 GB/s end to end).
+// shape: how the bytes are spread over the chunks.
+//   kEven     equal chunks;
+//   kTaper    encode: sizes fall geometrically (x 0.6).  What the call cannot overlap with anything is
+//             the copy back of its LAST chunk, and every launch pays the load imbalance of its few
+//             streams per warp once: few large chunks first, a small one at the end;
+//   kRamp     decode: the first two chunks are a quarter and a half of the others, so that the
+//             device-to-host copy (what the decode call is bound by) starts early.
+enum class ChunkShape { kEven, kTaper, kRamp };
+
 std::vector<uint64_t> chunk_bounds(const uint64_t* weight, uint64_t n, uint64_t chunk_bytes,
-                                   uint64_t min_streams) {
+                                   uint64_t min_streams, ChunkShape shape = ChunkShape::kEven) {
     const uint64_t total = weight[n] - weight[0];
     uint64_t chunks = total / chunk_bytes;
     if (min_streams && chunks > n / min_streams) chunks = n / min_streams;
     if (chunks < 1) chunks = 1;
     if (chunks > kMaxChunks) chunks = kMaxChunks;
     if (chunks > n) chunks = n;
+    // cumulative share of the bytes at the end of chunk c
+    std::vector<double> upto(chunks, 1.0);
+    if (shape == ChunkShape::kTaper && chunks >= 3) {
+        if (chunks > 6) chunks = 6;
+        upto.assign(chunks, 1.0);
+        double w = 1.0, sum = 0.0;
+        for (uint64_t c = 0; c < chunks; c++, w *= 0.6) sum += w;
+        double acc = 0.0;
+        w = 1.0;
+        for (uint64_t c = 0; c < chunks; c++, w *= 0.6) {
+            acc += w;
+            upto[c] = acc / sum;
+        }
+    } else if (shape == ChunkShape::kRamp && chunks >= 4) {
+        const double unit = 1.0 / ((double)chunks - 1.25);  // 0.25 + 0.5 + (chunks - 2) units
+        double acc = 0.0;
+        for (uint64_t c = 0; c < chunks; c++) {
+            acc += (c == 0 ? 0.25 : c == 1 ? 0.5 : 1.0) * unit;
+            upto[c] = acc;
+        }
+    } else {
+        for (uint64_t c = 0; c < chunks; c++) upto[c] = (double)(c + 1) / (double)chunks;
+    }
     std::vector<uint64_t> cb;
     cb.push_back(0);
     uint64_t i = 0;
-    for (uint64_t c = 1; c < chunks; c++) {
-        const uint64_t target = weight[0] + total / chunks * c;
+    for (uint64_t c = 0; c + 1 < chunks; c++) {
+        const uint64_t target = weight[0] + (uint64_t)((double)total * upto[c]);
         while (i < n && weight[i] < target) i++;
         if (i > cb.back() && i < n) cb.push_back(i);
     }
@@ -417,18 +453,21 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
     const std::vector<uint64_t> cb =
         chunk_bounds(needs_out && op == Op::Decode ? b->out_off : b->in_off, n,
                      op == Op::Encode ? ctx->enc_chunk_bytes : ctx->dec_chunk_bytes,
-                     ctx->chunk_min_streams ? (uint64_t)ctx->num_sms * (op == Op::Encode ? 28u : 32u) : 0u);
+                     ctx->chunk_min_streams ? (uint64_t)ctx->num_sms * (op == Op::Encode ? 28u : 32u) : 0u,
+                     op == Op::Encode ? ChunkShape::kTaper : ChunkShape::kRamp);
     const size_t chunks = cb.size() - 1;
     // encode: pinned input is read in place (the decoder's input is small and its access pattern
     // re-reads tiles, it stays staged)
     // (not with the predictor, which rewrites the device copy of the input)
     const bool predict = ctx->pred_row_bytes != 0 && needs_out;
     const uint8_t* in_alias =
-        (op == Op::Encode && ctx->zero_copy_in && !predict) ? device_alias(b->in) : nullptr;
+        (op == Op::Encode && ctx->zero_copy_in > 0 && !predict) ? device_alias(b->in) : nullptr;
 
+    const uint8_t* const in_alias_call = in_alias;
     auto enqueue = [&](size_t k) -> int {
         HostSlot& hs = ctx->pipe[k % kPipe];
         cudaStream_t s = hs.stream;
+        const uint8_t* const in_alias = (k == 0 || ctx->zero_copy_in >= 2) ? in_alias_call : nullptr;
         const uint64_t s0 = cb[k], s1 = cb[k + 1], m = s1 - s0;
         const uint64_t in_lo = b->in_off[s0], in_hi = b->in_off[s1];
         const uint64_t out_lo = needs_out ? b->out_off[s0] : 0, out_hi = needs_out ? b->out_off[s1] : 0;
@@ -539,11 +578,12 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
     const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->enc_chunk_bytes,
-                                                  ctx->chunk_min_streams ? (uint64_t)ctx->num_sms * 28u : 0u);
+                                                  ctx->chunk_min_streams ? (uint64_t)ctx->num_sms * 28u : 0u,
+                                                  ChunkShape::kTaper);
     const size_t chunks = cb.size() - 1;
     const bool predict = ctx->pred_row_bytes != 0;
     // pinned input is read in place, unless the predictor has to rewrite it on the device first
-    const uint8_t* in_alias = (ctx->zero_copy_in && !predict) ? device_alias(in) : nullptr;
+    const uint8_t* in_alias = (ctx->zero_copy_in > 0 && !predict) ? device_alias(in) : nullptr;
     uint64_t hbase = 0;  // dense bytes placed so far
     bool overflow = false;
     // deferred: device offsets of the chunks inside ctx->shard_dense (worst-case spacing)
@@ -559,9 +599,11 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         CK(ctx->shard_dense.reserve(dev_off[chunks] + 256), "cudaMalloc(dense shard)");
     }
 
+    const uint8_t* const in_alias_call = in_alias;
     auto enqueue = [&](size_t k) -> int {
         HostSlot& hs = ctx->pipe[k % kPipe];
         cudaStream_t s = hs.stream;
+        const uint8_t* const in_alias = (k == 0 || ctx->zero_copy_in >= 2) ? in_alias_call : nullptr;
         const uint64_t s0 = cb[k], s1 = cb[k + 1], m = s1 - s0;
         const uint64_t in_lo = in_off[s0], in_hi = in_off[s1];
         {
@@ -748,7 +790,7 @@ int slzw_create(int device, slzw_ctx** out) {
         encode_select_config(e ? atoi(e) : 0);
     }
     if (const char* e = getenv("SLZW_DEC_CONFIG")) decode_select_config(atoi(e));  // tuning knob
-    if (const char* e = getenv("SLZW_HOST_ZERO_COPY")) ctx->zero_copy_in = atoi(e) != 0;
+    if (const char* e = getenv("SLZW_HOST_ZERO_COPY")) ctx->zero_copy_in = atoi(e);
     if (const char* e = getenv("SLZW_HOST_CHUNK_BYTES")) {
         const long long v = atoll(e);  // tests use tiny chunks
         if (v > 0) {

@@ -118,6 +118,15 @@ int main(int argc, char** argv) {
         auto dec = decode_batch(packed.data(), poff, {lorem.size(), 0, d40.size()}, SLZW_FLAVOUR_VARIABLE, 8,
                                 Endianness::BigEndian, CodeSizeStrategy::Tiff);
         CHECK(dec[0].bytes == lorem && dec[1].bytes.empty() && dec[2].bytes == d40);
+        // the same batch over every GPU of the box: identical results
+        auto menc = multi::encode_batch(all.data(), off, SLZW_FLAVOUR_VARIABLE, 8, Endianness::BigEndian,
+                                        CodeSizeStrategy::Tiff);
+        CHECK(multi::device_count() >= 1 && menc.size() == 3);
+        for (size_t i = 0; i < menc.size() && i < enc.size(); i++)
+            CHECK(menc[i].bytes == enc[i].bytes && menc[i].status == enc[i].status);
+        auto mdec = multi::decode_batch(packed.data(), poff, {lorem.size(), 0, d40.size()}, SLZW_FLAVOUR_VARIABLE, 8,
+                                        Endianness::BigEndian, CodeSizeStrategy::Tiff);
+        CHECK(mdec[0].bytes == lorem && mdec[1].bytes.empty() && mdec[2].bytes == d40);
     }
     std::printf(failures ? "%d check(s) failed\n" : "all checks passed\n", failures);
     return failures ? 1 : 0;

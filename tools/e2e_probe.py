@@ -30,7 +30,7 @@ def main():
     h_dense = torch.empty(int(slots[-1]), dtype=torch.uint8).pin_memory().numpy()
     h_dec = torch.empty(total, dtype=torch.uint8).pin_memory().numpy()
     p = tiff_params()
-    for chunk, zc in ((0, 1), (0, 0), (400 << 20, 1), (800 << 20, 1), (1300 << 20, 1)):
+    for chunk, zc in ((0, 1),):
         os.environ.pop("SLZW_HOST_CHUNK_BYTES", None)
         if chunk:
             os.environ["SLZW_HOST_CHUNK_BYTES"] = str(chunk)
