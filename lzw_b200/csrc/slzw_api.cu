@@ -366,25 +366,14 @@ std::vector<uint64_t> chunk_bounds(const uint64_t* weight, uint64_t n, uint64_t 
     // cumulative share of the bytes at the end of chunk c
     std::vector<double> upto(chunks, 1.0);
     if (shape == ChunkShape::kTaper && chunks >= 3) {
-        // SLZW_HOST_TAPER_HEAD (experiment): relative size of an extra small first chunk, 0 = none
-        const char* he = getenv("SLZW_HOST_TAPER_HEAD");
-        const double head = he ? atof(he) : 0.0;
         if (chunks > 6) chunks = 6;
-        std::vector<double> w(chunks);
-        double v = 1.0, sum = 0.0;
-        for (uint64_t c = 0; c < chunks; c++) {
-            if (c == 0 && head > 0.0) {
-                w[c] = head;
-            } else {
-                w[c] = v;
-                v *= 0.6;
-            }
-            sum += w[c];
-        }
         upto.assign(chunks, 1.0);
+        double w = 1.0, sum = 0.0;
+        for (uint64_t c = 0; c < chunks; c++, w *= 0.6) sum += w;
         double acc = 0.0;
-        for (uint64_t c = 0; c < chunks; c++) {
-            acc += w[c];
+        w = 1.0;
+        for (uint64_t c = 0; c < chunks; c++, w *= 0.6) {
+            acc += w;
             upto[c] = acc / sum;
         }
     } else if (shape == ChunkShape::kRamp && chunks >= 4) {
