@@ -111,3 +111,38 @@ def test_multi_over_distinct_devices():
     dec, dlen, dstat, _ = mc.decode_batch(tiff_params(), dense, doff, off)
     assert np.array_equal(dec[: int(off[-1])], buf) or int((dstat != 0).sum()) > 0
     mc.close()
+
+
+def test_second_concurrent_host_call_on_one_context_is_refused():
+    """include/slzw.h: the *_host entry points of one context run one at a time; a call that arrives
+    while another one is running returns SLZW_RC_INVALID instead of interleaving the staging slots."""
+    import threading
+
+    import lzw_b200
+    from lzw_b200 import workloads as W
+    from lzw_b200.types import tiff_params
+    buf, off = W.tiff_strips(3000, seed=5)
+    slots = W.encode_slots(off)
+    codec = lzw_b200.Codec(0)
+    o_out, o_len, o_st, _ = O.encode_batch(O.tiff(), buf, off, slots, threads=8)
+    results, errors = [], []
+
+    def work():
+        for _ in range(6):
+            try:
+                out, _, out_len, st, det = codec.encode_batch(tiff_params(), buf, off, out_off=slots)
+                results.append((out_len.copy(), st.copy()))
+            except lzw_b200.codec.SlzwError as e:
+                errors.append(str(e))
+
+    threads = [threading.Thread(target=work) for _ in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert results, "no call went through"
+    for out_len, st in results:  # every call that ran is right
+        assert np.array_equal(out_len, o_len) and np.array_equal(st, o_st)
+    for e in errors:  # and every refused call says why
+        assert "rc=-2" in e and "in use by another host call" in e
+    codec.close()
