@@ -696,7 +696,10 @@ __global__ void __launch_bounds__((SW + GW) * kWarpSize, CTAS) slzw_decode_fast_
     __syncwarp();
     const bool global_table = warp >= SW;
     const uint64_t pol = l2_keep_policy();
-    for (;;) {
+    // a batch smaller than the grid's warps spreads over the SMs: only ceil(n / CTAs) warps per CTA
+    // take streams (the first ones, whose tables are in shared memory)
+    const uint32_t takers = (uint32_t)((a.n + gridDim.x - 1) / gridDim.x);
+    for (; (uint32_t)warp < takers;) {
         unsigned long long q = 0;
         if (lane == 0) q = atomicAdd(a.queue, 1ull);
         q = __shfl_sync(kFullMask, q, 0);
@@ -744,9 +747,9 @@ struct FastConfig {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem());
     }
     static cudaError_t launch(const DevBatch& a, int num_sms, cudaStream_t stream) {
-        const uint64_t ctas = (a.n + SW + GW - 1) / (SW + GW);
+        // one CTA per SM as soon as there is a stream for each (the kernel spreads a small batch)
         const uint64_t cap = (uint64_t)num_sms * CTAS;
-        const int grid = (int)(ctas < cap ? ctas : cap);
+        const int grid = (int)(a.n < cap ? a.n : cap);
         slzw_decode_fast_kernel<SW, GW, CTAS><<<grid, (SW + GW) * kWarpSize, smem(), stream>>>(a);
         return cudaGetLastError();
     }

@@ -1,5 +1,7 @@
 export PYTHONUNBUFFERED=1
-timeout 900 python -m pytest tests/test_gpu_stress.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
-for v in sync0 sync1 sync0 sync1; do
-  echo "== $v"; SLZW_LIB=$PWD/lzw_b200/csrc/variants/libslzw_$v.so timeout 300 python tools/enc_variants.py --streams 65536 --configs 2 --reps 5 2>&1 | tail -1 | cut -c1-120
+for v in tmemfirst smemfirst; do
+  echo "== $v"
+  for s in 512 1776; do SLZW_LIB=$PWD/lzw_b200/csrc/variants/libslzw_$v.so python tools/enc_variants.py --workload config4 --streams $s --configs 2 2>&1 | tail -1 | cut -c1-110; done
+  SLZW_LIB=$PWD/lzw_b200/csrc/variants/libslzw_$v.so python tools/enc_variants.py --workload config3 --streams 1776 --configs 2 2>&1 | tail -1 | cut -c1-110
+  SLZW_LIB=$PWD/lzw_b200/csrc/variants/libslzw_$v.so python tools/enc_variants.py --workload config5 --streams 1776 --configs 2 2>&1 | tail -1 | cut -c1-110
 done
