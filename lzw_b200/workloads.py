@@ -25,8 +25,9 @@ def _wl():
     global _WL
     if _WL is None:
         path = os.path.join(os.path.dirname(_HERE), "tools", "wlgen", "libwlgen.so")
-        if not os.path.exists(path):
-            raise RuntimeError(f"{path} is missing: run `python __graft_entry__.py` (build) first")
+        if not os.path.exists(path):  # a fresh checkout that skipped build(): one gcc call
+            import subprocess
+            subprocess.check_call(["make", "-C", os.path.dirname(path)])
         L = ctypes.CDLL(path)
         u64, vp = ctypes.c_uint64, ctypes.c_void_p
         L.wl_tiff_strip_lens.argtypes = [u64, u64, u64, u64, u64, vp]

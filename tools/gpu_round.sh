@@ -22,4 +22,4 @@ except Exception as e:
     print("no line:", e)
 P
 done
-tail -3 gpurun_out/*.err
+tail -n 3 gpurun_out/*.err
