@@ -9,10 +9,10 @@
 //     that `base | offset` needs no add);
 //   * warps 0..15 keep theirs in TENSOR MEMORY, which a codec otherwise never touches: 16 x 128
 //     columns of the SM's 512, accessed with tcgen05.ld / tcgen05.st (32x32b shapes).
-// x' = x * 0x9E5 mod 4096 is a bijection of the 12-bit codes ("scrambled" codes): dense sequential
-// codes would form runs under an XOR hash, scrambled ones do not, and prefix' ^ hash(byte) then
-// collides no more often than a 32-bit multiplicative hash of the whole key (measured,
-// profiles/r01_encode_notes.md).  Numbering of new entries is insertion order and lookups are
+// x' = x * kScr + kScrAdd mod 4096 is a bijection of the 12-bit codes ("scrambled" codes): dense
+// sequential codes would form runs under an XOR hash, scrambled ones do not, and prefix' ^ hash(byte)
+// then collides no more often than a 32-bit multiplicative hash of the whole key (measured,
+// profiles/r01_encode_notes.md; the constants of round 2: tools/exp/bucket_sim.c).  Numbering of new entries is insertion order and lookups are
 // exact (probing never gives up), so the emitted codes equal the reference's.
 //
 // Per stream:
@@ -51,21 +51,36 @@ namespace {
 
 constexpr int kSlots = 4096;
 constexpr uint32_t kBucketMask = 127u << 7;                   // byte offset of a 32-slot bucket
-constexpr uint32_t kScr = 0x9E5u;     // code -> code' = code * kScr mod 4096 (odd => bijection)
-constexpr uint32_t kScrInv = 0xBEDu;  // kScr * kScrInv == 1 mod 4096
-constexpr uint32_t kByteMul = 0x6A7u; // byte -> hash contribution
+constexpr uint32_t kScr = 0xC55u;     // code -> q = code * kScr + kScrAdd mod 4096 (odd => bijection)
+constexpr uint32_t kScrInv = 0xFDu;   // kScr * kScrInv == 1 mod 4096
+constexpr uint32_t kScrAdd = (0x1000u - ((255u * kScr) & 0xFFFu)) & 0xFFFu;
+constexpr uint32_t kUnscrAdd = (0x1000u - ((kScrAdd * kScrInv) & 0xFFFu)) & 0xFFFu;
+constexpr uint32_t kByteMul = 0x83Fu;     // byte -> bucket hash (bucket lookups)
+constexpr uint32_t kByteMulLat = 0x6A7u;  // byte -> bucket hash (latency variant)
 static_assert(((kScr * kScrInv) & 0xFFFu) == 1u, "kScrInv must invert kScr mod 4096");
+// the two properties the bucket lookups rest on (below)
+static_assert(((2u * kScr + kScrAdd) & 0xFFFu) == 0xFFFu, "q(2) must be 4095");
+static_assert(((255u * kScr + kScrAdd) & 0xFFFu) == 0u, "q(255) must be 0");
 
-// The bucket lookups (match_tile_bucket) keep codes as q = code' - 1 mod 4096 and store slots
-// complemented, ~(key | q), so that an empty slot is still 0: slot ^ ~key is then below 4095
-// exactly for the slot that holds the key (q == 4095 would be code 0, which is never a dictionary
-// value; an empty slot gives ~key, at least 4095), so ONE warp reduction, min over the 32 slots of
-// slot ^ ~key, answers "found?" and returns the new prefix at once -- no compare + ballot +
-// find-first + shuffle (profiles/r02_encode_notes.md).
+// The bucket lookups (match_tile_bucket) keep codes as q = code * kScr + kScrAdd mod 4096.  A
+// byte's record carries x = byte << 24 | q(byte), the prefix is a q, and the key of (prefix, byte) is
+//     k = prefix * 4096 + x  =  byte << 24 | prefix << 12 | q(byte)              -- ONE IMAD
+// (the low 12 bits are a function of the byte, so they take no part in telling two keys apart; a
+// prefix that still carries the byte << 24 of the record it was taken from loses it in the
+// multiplication).  The slot of an entry is ~(k ^ q(entry)); an empty slot is 0.  Then ~(slot ^ k)
+//   * is q(entry) for the slot that holds the key -- never 4095, which is q(2), and code 2 is a
+//     root for every code size, never a dictionary value;
+//   * has a bit above bit 11 set for a slot that holds another key;
+//   * is ~k for an empty slot: at least 4096 unless the key is byte 255 after the prefix with
+//     q = 4095, and exactly 4095 then, because q(255) = 0;
+// so ONE warp reduction, min over the 32 slots of ~(slot ^ k), answers "found?" (below 4095) and
+// IS the new prefix -- no compare + ballot + find-first + shuffle (profiles/r02_encode_notes.md).
+// An occupied slot is never 0 (it would need q(entry) = 4095).
 template <bool Q>
-__device__ __forceinline__ uint32_t scrq(uint32_t code) { return (code * kScr - (Q ? 1u : 0u)) & 0xFFFu; }
+__device__ __forceinline__ uint32_t scrq(uint32_t code) { return (code * kScr + (Q ? kScrAdd : 0u)) & 0xFFFu; }
 template <bool Q>
-__device__ __forceinline__ uint32_t unscrq(uint32_t e) { return (e * kScrInv + (Q ? kScrInv : 0u)) & 0xFFFu; }
+__device__ __forceinline__ uint32_t unscrq(uint32_t e) { return (e * kScrInv + (Q ? kUnscrAdd : 0u)) & 0xFFFu; }
+static_assert(((((7u * kScr + kScrAdd) & 0xFFFu) * kScrInv + kUnscrAdd) & 0xFFFu) == 7u, "unscrq must invert scrq");
 
 // Dictionary accesses by 32-bit shared-window address.  They are volatile asm statements so that
 // the compiler keeps them exactly where the match loop puts them (in particular the speculative
@@ -94,7 +109,7 @@ struct EncMisc {
     static constexpr int kRecs = TILE + 8;                      // + lookahead padding
     static constexpr int kCodeBuf = TILE + 16;                  // codes one tile can emit
     static constexpr int kOutWords = (kCodeBuf * 12) / 32 + 4;  // packed window
-    alignas(16) uint2 rec[kRecs];  // per input byte: {byte << 12, hash bits | table base}
+    alignas(16) uint2 rec[kRecs];  // per input byte: {byte << 24 | q(byte), hash bits | table base} (latency variant: byte << 12)
     uint32_t outw[kOutWords];
     uint16_t codes[kCodeBuf];  // [width:4 | code':12]
 };
@@ -134,6 +149,18 @@ __device__ __forceinline__ uint32_t bucket_row_addr(uint32_t row0, uint32_t pref
     asm("lop3.b32 %0, %1, %2, 0x7F, 0x28;\n" : "=r"(x) : "r"(prefix), "r"(h7));  // (prefix ^ h7) & 0x7F
     asm("mad.lo.u32 %0, %1, 128, %2;\n" : "=r"(a) : "r"(x), "r"(row0));
     return a;
+}
+
+// ~(a ^ b) and ~(a ^ (b & 0xFFF)) as ONE LOP3 each (the compiler emits XOR + NOT)
+__device__ __forceinline__ uint32_t xnor32(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, 0, 0xC3;\n" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t xnor_low12(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, 0xFFF, 0x87;\n" : "=r"(d) : "r"(a), "r"(b));
+    return d;
 }
 
 // index of the most significant set bit (FLO)
@@ -199,7 +226,7 @@ __device__ __forceinline__ void tmem_clear(uint32_t tbase) {
 // that owns the first empty slot inserts it); a full bucket overflows into the next one.  There is
 // no separate collision path and no speculation: 1.00 to 1.14 bucket loads per input byte on the
 // config-3 strips at the format's load factor of up to 0.94 (profiles/r01_encode_notes.md).
-// rec[i] = {byte << 12 | q(byte), hash7(byte)} (shared memory) or {byte << 12 | q(byte), dictionary's
+// rec[i] = {byte << 24 | q(byte), hash7(byte)} (shared memory) or {byte << 24 | q(byte), dictionary's
 // tensor-memory address | hash7(byte)} (tensor memory); `tl` = shared address of this lane's slot
 // in bucket 0, `tb` = tensor-memory address of the dictionary.
 // MODE says what a miss may have to do in this tile (chosen per tile by the caller from the
@@ -218,8 +245,9 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                                                   const uint32_t cs, const uint32_t inc,
                                                   const uint32_t clear_code,
                                                   const uint32_t first_code) {
-    uint32_t t = m.t;                             // prefix' << 20: key position
-    uint32_t tp = m.t >> 20;                      // prefix (q): its low 7 bits choose the bucket
+    // prefix (q): its low 7 bits choose the bucket, its low 12 bits go into the key and are the
+    // code a miss emits; after a miss it is the record's x, byte << 24 | q(byte), as it stands
+    uint32_t tp = m.t >> 20;
     uint32_t ncs = m.ncs;                         // low 12 bits count, upper bits are garbage
     uint32_t ws = FIXED ? 12u : m.ws;
     uint32_t wtag = ws << 12;
@@ -239,9 +267,9 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
 
 #define SLZW_STEP_B(RC)                                                                         \
     {                                                                                           \
-        /* slots hold ~(key | q): an empty slot is 0 and slot ^ ~key is q for the slot that   \
+        /* slots hold ~(key ^ q): an empty slot is 0 and ~(slot ^ key) is q for the slot that   \
            holds the key, at least 4095 for every other one */                                   \
-        const uint32_t key = ~(t | ((RC).x & 0xFF000u));                                        \
+        const uint32_t key = tp * 4096u + (RC).x;                                               \
         uint32_t a = TMEM ? ((tp & 0x7Fu) ^ (RC).y) : bucket_row_addr(tlr, tp, (RC).y);         \
         /* Both bucket loads (tcgen05.ld, ldmatrix) are .sync.aligned: the warp is converged at   \
            every step, the compiler puts no divergence guard in front of the ballots and the     \
@@ -258,19 +286,16 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
             /* q of the entry iff my slot holds the key, at least 4095 otherwise; the minimum   \
                over the bucket (one REDUX) says "found" and is the new prefix */                 \
             if (SLZW_HIT_REDUX) {                                                               \
-                const uint32_t c = __reduce_min_sync(kFullMask, v ^ key);                       \
+                const uint32_t c = __reduce_min_sync(kFullMask, xnor32(v, key));                     \
                 if (c < 4095u) { /* find_word hit, encoder.rs:319-320 */                        \
-                    t = c << 20;                                                                \
                     tp = c;                                                                     \
                     break;                                                                      \
                 }                                                                               \
             } else {                                                                            \
-                const uint32_t x = v ^ key;                                                     \
+                const uint32_t x = xnor32(v, key);                                             \
                 const uint32_t bal = __ballot_sync(kFullMask, x < 4095u);                       \
                 if (bal) {                                                                      \
-                    const uint32_t c = __shfl_sync(kFullMask, x, (int)bfind(bal));              \
-                    t = c << 20;                                                                \
-                    tp = c;                                                                     \
+                    tp = __shfl_sync(kFullMask, x, (int)bfind(bal));                            \
                     break;                                                                      \
                 }                                                                               \
             }                                                                                   \
@@ -281,12 +306,12 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                 continue;                                                                       \
             }                                                                                   \
             /* miss: encoder.rs:322-324 / 645-649 */                                            \
-            /* the prefix' being emitted: tp itself in the tensor-memory variant */             \
-            sts_u16(cpa, MODE == 1 ? ((TMEM ? tp : t >> 20) | wtag) : (TMEM ? tp : t >> 20));   \
+            /* the prefix being emitted: the low 16 bits of tp hold nothing else */             \
+            sts_u16(cpa, MODE == 1 ? (tp | wtag) : tp);                                         \
             cpa += 2u;                                                                          \
             if (MODE == 0 || (MODE == 1 && (!FIXED || until != 0u))) {                          \
                 const bool mine = em == lanes_ge; /* I own the first empty slot */              \
-                const uint32_t entry = key & ~(ncs & 0xFFFu);                                   \
+                const uint32_t entry = xnor_low12(key, ncs);                                     \
                 if (TMEM) {                                                                     \
                     tmem_st(a, mine ? entry : v);                                               \
                     tmem_wait_st();                                                             \
@@ -325,15 +350,38 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
                     }                                                                           \
                 }                                                                               \
             }                                                                                   \
-            /* prefix = this byte: its q sits in the low bits of the record (only the low 7   \
-               bits of tp / bits 7..13 of tp << 7 reach the bucket address) */                   \
-            t = (RC).x << 20;                                                                   \
-            tp = (RC).x & 0xFFFu;                                                               \
+            /* prefix = this byte: its q sits in the low bits of the record */                  \
+            tp = (RC).x;                                                                        \
             break;                                                                              \
         }                                                                                       \
     }
 
     uint32_t i = 0;
+    if constexpr (U >= 8) {
+        while (i + 8u <= len) {
+            {
+                const uint4 ra = *reinterpret_cast<const uint4*>(rec + i);
+                const uint4 rb = *reinterpret_cast<const uint4*>(rec + i + 2);
+                const uint2 r0 = make_uint2(ra.x, ra.y), r1 = make_uint2(ra.z, ra.w);
+                const uint2 r2 = make_uint2(rb.x, rb.y), r3 = make_uint2(rb.z, rb.w);
+                SLZW_STEP_B(r0)
+                SLZW_STEP_B(r1)
+                SLZW_STEP_B(r2)
+                SLZW_STEP_B(r3)
+            }
+            {
+                const uint4 ra = *reinterpret_cast<const uint4*>(rec + i + 4);
+                const uint4 rb = *reinterpret_cast<const uint4*>(rec + i + 6);
+                const uint2 r0 = make_uint2(ra.x, ra.y), r1 = make_uint2(ra.z, ra.w);
+                const uint2 r2 = make_uint2(rb.x, rb.y), r3 = make_uint2(rb.z, rb.w);
+                SLZW_STEP_B(r0)
+                SLZW_STEP_B(r1)
+                SLZW_STEP_B(r2)
+                SLZW_STEP_B(r3)
+            }
+            i += 8u;
+        }
+    }
     if constexpr (U >= 4) {
         while (i + 4u <= len) {
             // four records with two 128-bit loads (i is a multiple of 4, rec is 16-byte aligned)
@@ -367,7 +415,7 @@ __device__ __forceinline__ void match_tile_bucket(uint32_t* __restrict__ table, 
 #undef SLZW_STEP_B
 
     if (MODE == 0) until -= (cpa - cpa0) >> 1;  // one insert per emitted code
-    m.t = t;
+    m.t = tp << 20;
     m.ncs = ncs & 0xFFFu;
     m.ws = ws;
     m.mask = mask;
@@ -502,6 +550,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     using Misc = EncMisc<TILE>;
     static_assert(TILE % 4 == 0 && TILE <= 4 * kWarpSize, "one 32-bit word per lane");
     uint2* __restrict__ rec = S.rec;
+    constexpr int kRecByteShift = LAT ? 12 : 24;  // where a record's x holds the byte
     uint16_t* __restrict__ codes = S.codes;
     uint32_t* __restrict__ outw = S.outw;
     const uint64_t in_begin = a.in_off[sid];
@@ -565,21 +614,25 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
     };
 
     // Whole warp: bit-pack the buffered codes, flush complete words.
-    // An entry without a width tag (stored by a match loop that cannot meet a width change) takes
-    // the width `wdef`.
-    auto pack_and_flush = [&](uint32_t count, uint32_t wdef) {
+    // An entry without a width tag (stored by a match loop that does not track the width) takes
+    // the width `wdef` in front of buffer index `split` and `wdef + 1` from there on (the one width
+    // bump such a tile may contain, see below).
+    auto pack_and_flush = [&](uint32_t count, uint32_t wdef, uint32_t split = ~0u) {
         for (uint32_t base = 0; base < count; base += kWarpSize) {
             const uint32_t idx = base + lane;
             const uint32_t e = idx < count ? codes[idx] : 0u;
-            const uint32_t wd = idx < count ? ((e >> 12) ? (e >> 12) : wdef) : 0u;
+            const uint32_t w0 = base < split ? wdef : wdef + 1u;  // untagged width at the round's start
+            const bool mixed = split > base && split < base + (uint32_t)kWarpSize;  // ... changes inside it
+            const uint32_t wu = idx < split ? wdef : wdef + 1u;
+            const uint32_t wd = idx < count ? ((e >> 12) ? (e >> 12) : wu) : 0u;
             const uint32_t code = unscrq<true>(e) & ((1u << wd) - 1u);  // BitWriter masks to the width
-            // inclusive prefix sum of the widths; codes without a tag all have the tile's width,
-            // which is the common case (MODE 0 / 2 tiles) and needs no scan
+            // inclusive prefix sum of the widths; codes without a tag all have the same width in
+            // nearly every round (MODE 0 / 2 tiles), which needs no scan
             uint32_t x, total;
-            if (!__any_sync(kFullMask, (e >> 12) != 0u)) {
+            if (!mixed && !__any_sync(kFullMask, (e >> 12) != 0u)) {
                 const uint32_t left = count - base;
-                x = ((uint32_t)lane + 1u) * wdef;
-                total = (left < (uint32_t)kWarpSize ? left : (uint32_t)kWarpSize) * wdef;
+                x = ((uint32_t)lane + 1u) * w0;
+                total = (left < (uint32_t)kWarpSize ? left : (uint32_t)kWarpSize) * w0;
             } else {
                 x = wd;
 #pragma unroll
@@ -651,9 +704,9 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
             const uint32_t k = (w >> (8 * b)) & 0xFFu;
             if (idx < tile_len) {
                 const uint32_t h7 = ((k * kByteMul) >> 2) & 0x7Fu;
-                // bucket lookups: the low 12 bits carry q of the byte itself (the prefix after a miss)
-                rec[idx] = make_uint2((k << 12) | scrq<true>(k), TMEM ? (tb | h7)
-                                               : LAT ? (((k * kByteMul) << 5) & 0x3FE0u)
+                // the low 12 bits carry q of the byte itself (the prefix after a miss)
+                rec[idx] = make_uint2((k << kRecByteShift) | scrq<true>(k), TMEM ? (tb | h7)
+                                               : LAT ? (((k * kByteMulLat) << 5) & 0x3FE0u)
                                                      : h7);
                 if (!FIXED && k > max_code && idx < bad) bad = idx;
             }
@@ -673,9 +726,24 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
         __syncwarp();
 
         const uint32_t ws_tile = m.ws;  // width of the codes a MODE 0 / 2 tile stores without a tag
+        uint32_t split = ~0u;           // buffer index of the first untagged code of width ws_tile + 1
         if (len) {
             // inserts left before the next event against the most this tile can insert
-            const int mode = (FIXED && m.until == 0u) ? 2 : (m.until > len ? 0 : 1);
+            int mode = (FIXED && m.until == 0u) ? 2 : (m.until > len ? 0 : 1);
+            // A width bump (encoder.rs:327-328) changes nothing but the width of the codes that
+            // follow it: a tile that can meet ONE bump and nothing else runs the MODE 0 loop, the
+            // packer takes the new width from the until-th code of the tile on, and the state is
+            // brought up to date below.  Left to MODE 1: the reset at 12 bits and tiles that could
+            // meet two events (small code sizes at the start of a stream).
+            bool bump = false;
+            if (!FIXED && !LAT && mode == 1 && m.ws < 12u) {
+                const uint32_t nm = (2u << m.ws) - inc;  // size_increase_mask after the bump
+                if (m.until + (nm - m.mask) > len) {
+                    bump = true;
+                    split = m.ncodes + m.until;
+                    mode = 0;
+                }
+            }
             // unroll of the MODE 0 and MODE 2 loops: 4 steps per iteration amortise the loop's own
             // instructions (81.9 against 85.0 ms at config 3, 51.7 against 53.7 ms at config 5);
             // 8 spill and run at 90.6 ms.  MODE 1 tiles are rare and keep U.
@@ -695,10 +763,17 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
                 else if constexpr (FIXED) SLZW_MATCH_B(false, 2);
             }
 #undef SLZW_MATCH_B
+            // MODE 0 left until = until - inserts (mod 2^32); the until-th insert was the bump
+            if (bump && (int32_t)m.until <= 0) {
+                m.ws++;
+                const uint32_t nm = (1u << m.ws) - inc;
+                m.until += nm - m.mask;
+                m.mask = nm;
+            }
         }
         __syncwarp();
 
-        pack_and_flush(m.ncodes, ws_tile);
+        pack_and_flush(m.ncodes, ws_tile, split);
         m.ncodes = 0;
         // The `&mut [u8]` writer fails at the first byte past the slot (io.rs:244 / 307).  Codes
         // are emitted in input order, so a write failure inside this tile precedes a rejected
@@ -707,7 +782,7 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
             status = SLZW_ERR_IO_WRITE_ZERO;
         } else if (len < tile_len) {
             status = SLZW_ERR_UNEXPECTED_CODE;
-            detail = (rec[len].x >> 12) & 0xFFu;
+            detail = (rec[len].x >> kRecByteShift) & 0xFFu;
         }
         pos = npos;
         tile_len = nlen;

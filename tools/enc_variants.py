@@ -80,10 +80,12 @@ def main():
         else:
             ok = all(torch.equal(a, b) for a, b in zip(ref, res))
         ms = float(np.median(times))
+        import hashlib
+        digest = hashlib.sha256(d_dense[:total].cpu().numpy()).hexdigest()[:16]  # compares builds (SLZW_LIB)
         shares = codec.last_encode_shares()
         print(json.dumps({"config": cfg, "workload": args.workload, "streams": n, "ms": round(ms, 3),
                           "GBps_uncompressed": round(buf.size / ms / 1e6, 2), "compressed": total,
-                          "errors": int((d_st != 0).sum().item()), "matches_first": ok,
+                          "errors": int((d_st != 0).sum().item()), "matches_first": ok, "sha256_16": digest,
                           "GBps_by_kind[tmem_warp,smem_warp,smem_lanes,global_lanes]": [round(float(x) / ms / 1e6, 2) for x in shares]}), flush=True)
         codec.close()
 
