@@ -12,6 +12,7 @@
 #include <atomic>
 #include <mutex>
 #include <new>
+#include <chrono>
 #include <vector>
 
 #include "slzw_device.cuh"
@@ -86,7 +87,7 @@ struct Workspace {
 
 constexpr int kWorkspaces = 4;
 constexpr size_t kQueueWords = 8;  // [4..7]: input bytes encoded per kind of warp (diagnostics)
-constexpr int kPipe = 3;
+constexpr int kPipe = 4;
 // host-path chunks: at least this many input/output bytes each (a chunk must amortise the tail
 // of its longest stream), at most kMaxChunks per call
 // measured on config 3 (profiles/r01_e2e_notes.md): the encoder wants larger chunks (every chunk
@@ -128,7 +129,48 @@ struct HostSlot {
     }
 };
 
+// Streams and events of the dense encode pipeline (run_host_encode_dense), created on first use.
+struct EncPipe {
+    cudaStream_t in = nullptr, small = nullptr, dense = nullptr, cmp[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[kPipe] = {}, ev_enc[kPipe] = {}, ev_cmp[kPipe] = {}, ev_small[kPipe] = {}, ev_out[kPipe] = {};
+    bool used[kPipe] = {};
+    bool ready = false;
+    cudaError_t create() {
+        if (ready) return cudaSuccess;
+        cudaError_t e;
+        for (cudaStream_t* st : {&in, &small, &dense, &cmp[0], &cmp[1]})
+            if ((e = cudaStreamCreateWithFlags(st, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        for (int i = 0; i < kPipe; i++)
+            for (cudaEvent_t* ev : {&ev_in[i], &ev_enc[i], &ev_cmp[i], &ev_small[i], &ev_out[i]})
+                if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+        ready = true;
+        return cudaSuccess;
+    }
+    void sync_all() {
+        for (cudaStream_t st : {in, small, dense, cmp[0], cmp[1]})
+            if (st) cudaStreamSynchronize(st);
+    }
+    void release() {
+        for (cudaStream_t* st : {&in, &small, &dense, &cmp[0], &cmp[1]}) {
+            if (*st) cudaStreamDestroy(*st);
+            *st = nullptr;
+        }
+        for (int i = 0; i < kPipe; i++)
+            for (cudaEvent_t* ev : {&ev_in[i], &ev_enc[i], &ev_cmp[i], &ev_small[i], &ev_out[i]}) {
+                if (*ev) cudaEventDestroy(*ev);
+                *ev = nullptr;
+            }
+        ready = false;
+    }
+};
+
 }  // namespace
+
+// ChunkShape::kHill (below): first chunk in MiB, ratio of the second to the first, growth of the
+// following ones up to the chunk size, taper after it
+struct HillShape {
+    double first_mb = 96, second = 2.0, grow = 1.36, taper = 0.62;
+};
 
 struct slzw_ctx {
     int device = 0;
@@ -139,11 +181,14 @@ struct slzw_ctx {
     // chunk of streams, the kernels of the previous chunk and the D2H copy of the one before
     // overlap (PCIe is full duplex)
     HostSlot pipe[kPipe];
+    EncPipe enc_pipe;  // streams and events of the dense encode pipeline
     // pinned encoder input read in place by the kernels instead of staged (SLZW_HOST_ZERO_COPY): 0
     // never; 1 (default) the first chunk of a call only -- the one chunk whose staging copy nothing
     // hides; the kernels read host memory at 23 GB/s, the copy engine stages it at 55 GB/s
     // (profiles/r02_e2e_notes.md); 2 every chunk
     int zero_copy_in = 1;
+    int enc_shape = 0;  // 0 taper, 1 hill (SLZW_HOST_ENC_HILL="first_mb:second:grow:taper")
+    HillShape hill;
     bool chunk_min_streams = true;  // off when SLZW_HOST_CHUNK_BYTES is set (tests force tiny chunks)
     uint64_t enc_chunk_bytes = kEncChunkBytes;
     uint64_t dec_chunk_bytes = kDecChunkBytes;
@@ -353,11 +398,48 @@ const uint8_t* device_alias(const void* p) {
 //             streams per warp once: few large chunks first, a small one at the end;
 //   kRamp     decode: the first two chunks are a quarter and a half of the others, so that the
 //             device-to-host copy (what the decode call is bound by) starts early.
-enum class ChunkShape { kEven, kTaper, kRamp };
+//   kHill     encode: small first chunk (read in place while nothing else could hide its copy),
+//             sizes growing as fast as the copy of the next chunk hides behind the kernel of the
+//             current one, a plateau of chunk_bytes, then the taper.
+enum class ChunkShape { kEven, kTaper, kRamp, kHill };
 
 std::vector<uint64_t> chunk_bounds(const uint64_t* weight, uint64_t n, uint64_t chunk_bytes,
-                                   uint64_t min_streams, ChunkShape shape = ChunkShape::kEven) {
+                                   uint64_t min_streams, ChunkShape shape = ChunkShape::kEven,
+                                   const HillShape* hill = nullptr) {
     const uint64_t total = weight[n] - weight[0];
+    if (shape == ChunkShape::kHill && hill && n >= 2 && total > 0) {
+        // sizes in bytes: ramp, plateau, taper; scaled to the total at the end
+        const double first = hill->first_mb * 1048576.0, peak = (double)chunk_bytes;
+        std::vector<double> up, down;
+        for (double c = first; c < peak && up.size() < 12; c *= (up.empty() ? hill->second : hill->grow)) up.push_back(c);
+        for (double c = peak * hill->taper; c >= first && down.size() < 12; c *= hill->taper) down.push_back(c);
+        auto sum = [](const std::vector<double>& v) { double a = 0; for (double x : v) a += x; return a; };
+        // a total too small for the whole hill loses its top
+        while (sum(up) + sum(down) > (double)total && up.size() + down.size() > 1) {
+            if (!down.empty() && (up.empty() || down.front() >= up.back())) down.erase(down.begin());
+            else up.pop_back();
+        }
+        const double rest = (double)total - sum(up) - sum(down);
+        uint64_t plateau = rest > 0 ? (uint64_t)(rest / peak + 0.5) : 0;
+        std::vector<double> sizes(up);
+        for (uint64_t i = 0; i < plateau && sizes.size() + down.size() < kMaxChunks; i++) sizes.push_back(peak);
+        sizes.insert(sizes.end(), down.begin(), down.end());
+        const double all = sum(sizes);
+        std::vector<uint64_t> cb;
+        cb.push_back(0);
+        uint64_t i = 0;
+        double acc = 0;
+        for (size_t c = 0; c + 1 < sizes.size(); c++) {
+            acc += sizes[c];
+            const uint64_t target = weight[0] + (uint64_t)((double)total * (acc / all));
+            while (i < n && weight[i] < target) i++;
+            // a chunk that does not fill the device is merged into the next one
+            if (i < n && i >= cb.back() + (min_streams ? min_streams / 2 : 1)) cb.push_back(i);
+        }
+        if (n - cb.back() < (min_streams ? min_streams / 2 : 1) && cb.size() > 1) cb.pop_back();
+        cb.push_back(n);
+        return cb;
+    }
     uint64_t chunks = total / chunk_bytes;
     if (min_streams && chunks > n / min_streams) chunks = n / min_streams;
     if (chunks < 1) chunks = 1;
@@ -550,8 +632,20 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
 }
 
 // Host path with dense output: worst-case slots stay on the device, compaction before D2H, so
-// only encoded bytes cross the bus.  Pipelined like run_host; the host learns a chunk's dense
-// size when its kernels are done, places the chunk behind the previous one and starts its copy.
+// only encoded bytes cross the bus.  The host learns a chunk's dense size when its kernels are
+// done, places the chunk behind the previous one and starts its copy.
+//
+// An encode CTA takes its SM whole (all registers, all shared memory), so nothing else runs beside
+// it: while an encode kernel that is ready to run is queued anywhere, the compaction of the chunk
+// before it does not get an SM until that kernel has drained, and whatever the host issues after
+// waiting for the compaction (the next input copy) starts that much later -- measured as 8 ms of
+// idle device per two chunks with one stream per chunk (profiles/r02_e2e_notes.md).  Hence:
+//   * one stream copies the inputs of up to kPipe chunks ahead, gated by nothing but buffer reuse;
+//   * chunks alternate between TWO compute streams, each running encode then compaction: the
+//     encode kernel of chunk k+2 is ordered behind the compaction of chunk k, so the compaction
+//     gets the SMs that the draining encode kernel of chunk k+1 sets free, and chunk k+2 follows;
+//   * the small read-backs (sizes, statuses) and the dense copies have a stream each: a read-back
+//     never waits in stream order for the host to place an earlier chunk.
 // deferred: the dense chunks stay in ctx->shard_dense (worst-case spacing) and only sizes, statuses
 // and details come back; run_host_dense_finish copies them out later.
 int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
@@ -577,13 +671,20 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     NvtxRange range("slzw encode batch, dense (host pipeline)");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
+    EncPipe& ep = ctx->enc_pipe;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        CK(ep.create(), "cudaStreamCreate / cudaEventCreate (encode pipeline)");
+    }
     const std::vector<uint64_t> cb = chunk_bounds(in_off, n, ctx->enc_chunk_bytes,
                                                   ctx->chunk_min_streams ? (uint64_t)ctx->num_sms * 28u : 0u,
-                                                  ChunkShape::kTaper);
+                                                  ctx->enc_shape == 1 ? ChunkShape::kHill : ChunkShape::kTaper,
+                                                  &ctx->hill);
     const size_t chunks = cb.size() - 1;
     const bool predict = ctx->pred_row_bytes != 0;
-    // pinned input is read in place, unless the predictor has to rewrite it on the device first
-    const uint8_t* in_alias = (ctx->zero_copy_in > 0 && !predict) ? device_alias(in) : nullptr;
+    // the first chunk of pinned input may be read in place (nothing could hide its copy), unless
+    // the predictor has to rewrite it on the device first
+    const uint8_t* const in_alias_call = (ctx->zero_copy_in > 0 && !predict) ? device_alias(in) : nullptr;
     uint64_t hbase = 0;  // dense bytes placed so far
     bool overflow = false;
     // deferred: device offsets of the chunks inside ctx->shard_dense (worst-case spacing)
@@ -599,10 +700,39 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         CK(ctx->shard_dense.reserve(dev_off[chunks] + 256), "cudaMalloc(dense shard)");
     }
 
-    const uint8_t* const in_alias_call = in_alias;
+    // SLZW_HOST_TRACE=1 (debugging aid): timeline of the call, one line per chunk on stderr.
+    // Every event is recorded right behind an operation of its own stream (an event in front of
+    // the first copy of a stream queues behind whatever the stream's last engine is doing).
+    const bool trace = getenv("SLZW_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    std::vector<double> t_enq(chunks, 0.0), t_placed(chunks, 0.0);
+    const auto t_call = std::chrono::steady_clock::now();
+    auto host_ms = [&]() {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+    };
+    if (trace) {
+        tev.resize(chunks * 4 + 1);
+        for (auto& e : tev) cudaEventCreate(&e);
+        cudaEventRecord(tev[chunks * 4], ep.in);
+    }
+    auto mark = [&](size_t k, int what, cudaStream_t st) {
+        if (trace) cudaEventRecord(tev[k * 4 + what], st);
+    };
+    auto fail = [&](int rc) {
+        ep.sync_all();
+        for (auto& e : tev) cudaEventDestroy(e);
+        return drain_pipe(ctx, rc);
+    };
+#define CKP(call, what)                                             \
+    do {                                                            \
+        cudaError_t e_ = (call);                                    \
+        if (e_ != cudaSuccess) return fail(fail_cuda(ctx, e_, what)); \
+    } while (0)
+
     auto enqueue = [&](size_t k) -> int {
-        HostSlot& hs = ctx->pipe[k % kPipe];
-        cudaStream_t s = hs.stream;
+        const int slot = (int)(k % kPipe);
+        HostSlot& hs = ctx->pipe[slot];
+        cudaStream_t sc = ep.cmp[k & 1];
         const uint8_t* const in_alias = (k == 0 || ctx->zero_copy_in >= 2) ? in_alias_call : nullptr;
         const uint64_t s0 = cb[k], s1 = cb[k + 1], m = s1 - s0;
         const uint64_t in_lo = in_off[s0], in_hi = in_off[s1];
@@ -634,13 +764,22 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
             CK(hs.detail.reserve(sizeof(uint32_t) * m), "cudaMalloc(detail)");
             if (code_size) CK(hs.cs.reserve(m), "cudaMalloc(code_size)");
         }
+        if (trace) t_enq[k] = host_ms();
+        // input: the slot's previous chunk (k - kPipe) was placed before this call, so its kernels
+        // are done with these buffers
         if (!in_alias && in_hi > in_lo)
-            CK(cudaMemcpyAsync(hs.in.p, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
-        CK(cudaMemcpyAsync(hs.in_off.p, st.in_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
+            CK(cudaMemcpyAsync(hs.in.p, in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, ep.in), "H2D in");
+        CK(cudaMemcpyAsync(hs.in_off.p, st.in_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, ep.in),
            "H2D in_off");
-        CK(cudaMemcpyAsync(hs.out_off.p, st.out_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
+        CK(cudaMemcpyAsync(hs.out_off.p, st.out_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, ep.in),
            "H2D slots");
-        if (code_size) CK(cudaMemcpyAsync(hs.cs.p, st.cs, m, cudaMemcpyHostToDevice, s), "H2D code_size");
+        if (code_size) CK(cudaMemcpyAsync(hs.cs.p, st.cs, m, cudaMemcpyHostToDevice, ep.in), "H2D code_size");
+        CK(cudaEventRecord(ep.ev_in[slot], ep.in), "cudaEventRecord");
+        mark(k, 1, ep.in);
+        // kernels
+        CK(cudaStreamWaitEvent(sc, ep.ev_in[slot], 0), "cudaStreamWaitEvent");
+        // the dense copy of the slot's previous chunk must have left the dense buffer
+        if (ep.used[slot] && !deferred) CK(cudaStreamWaitEvent(sc, ep.ev_out[slot], 0), "cudaStreamWaitEvent");
         slzw_batch d = {};
         d.in = in_alias ? in_alias : (const uint8_t*)hs.in.p - in_lo;
         d.in_off = (const uint64_t*)hs.in_off.p;
@@ -653,26 +792,32 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         d.n = m;
         if (predict) {
             CK(predictor_launch(0, (uint8_t*)hs.in.p - in_lo, d.in_off, nullptr, m, ctx->pred_row_bytes,
-                                ctx->pred_spp, ctx->num_sms, s), "predictor launch");
+                                ctx->pred_spp, ctx->num_sms, sc), "predictor launch");
             ctx->launches += 1;
         }
-        int rc = run_device(ctx, params, &d, s, Op::Encode);
+        int rc = run_device(ctx, params, &d, sc, Op::Encode);
         if (rc != SLZW_RC_OK) return rc;
         CK(compact_launch(d.out, d.out_off, d.out_len, m, align,
                           deferred ? (uint8_t*)ctx->shard_dense.p + dev_off[k] : (uint8_t*)hs.dense.p,
-                          (uint64_t*)hs.dense_off.p, ctx->num_sms, s), "compaction launch");
+                          (uint64_t*)hs.dense_off.p, ctx->num_sms, sc), "compaction launch");
         ctx->launches += 2;
+        CK(cudaEventRecord(ep.ev_cmp[slot], sc), "cudaEventRecord");
+        mark(k, 2, sc);
         // the chunk's dense offsets come back in the out_len area of the stage (m + 1 entries)
-        CK(cudaMemcpyAsync(st.out_len, hs.dense_off.p, sizeof(uint64_t) * (m + 1), cudaMemcpyDeviceToHost, s),
+        CK(cudaStreamWaitEvent(ep.small, ep.ev_cmp[slot], 0), "cudaStreamWaitEvent");
+        CK(cudaMemcpyAsync(st.out_len, hs.dense_off.p, sizeof(uint64_t) * (m + 1), cudaMemcpyDeviceToHost, ep.small),
            "D2H dense_off");
-        CK(cudaMemcpyAsync(st.status, hs.status.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H status");
-        CK(cudaMemcpyAsync(st.detail, hs.detail.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H detail");
+        CK(cudaMemcpyAsync(st.status, hs.status.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, ep.small), "D2H status");
+        CK(cudaMemcpyAsync(st.detail, hs.detail.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, ep.small), "D2H detail");
+        CK(cudaEventRecord(ep.ev_small[slot], ep.small), "cudaEventRecord");
+        ep.used[slot] = true;
         return SLZW_RC_OK;
     };
     // chunk k's kernels are done: place it behind chunk k-1 and start the copy of its bytes
     auto place = [&](size_t k) -> int {
-        HostSlot& hs = ctx->pipe[k % kPipe];
-        CK(cudaStreamSynchronize(hs.stream), "cudaStreamSynchronize");
+        const int slot = (int)(k % kPipe);
+        HostSlot& hs = ctx->pipe[slot];
+        CK(cudaEventSynchronize(ep.ev_small[slot]), "cudaEventSynchronize");
         const uint64_t s0 = cb[k], m = cb[k + 1] - cb[k];
         ChunkStage st;
         st.bind(hs.stage.p, m);
@@ -685,23 +830,40 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         } else {
             if (hbase + total > out_cap) overflow = true;
             if (!overflow && total)
-                CK(cudaMemcpyAsync(out_dense + hbase, hs.dense.p, total, cudaMemcpyDeviceToHost, hs.stream),
+                CK(cudaMemcpyAsync(out_dense + hbase, hs.dense.p, total, cudaMemcpyDeviceToHost, ep.dense),
                    "D2H dense");
+            CK(cudaEventRecord(ep.ev_out[slot], ep.dense), "cudaEventRecord");
         }
+        if (trace) t_placed[k] = host_ms();
+        mark(k, 3, ep.dense);
         hbase += total;
         return SLZW_RC_OK;
     };
 
     int rc;
+    // up to kPipe chunks in flight; chunk k + kPipe takes the slot of chunk k once that is placed
+    for (size_t k = 0; k < chunks && k < (size_t)kPipe; k++)
+        if ((rc = enqueue(k)) != SLZW_RC_OK) return fail(rc);
     for (size_t k = 0; k < chunks; k++) {
-        if ((rc = enqueue(k)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
-        // chunks are placed in order, one chunk behind the newest launch; the slot chunk k+1 will
-        // use (that of chunk k+1-kPipe) has been placed by then and its copy is ordered before
-        // the reuse by the slot's stream
-        if (k >= 1 && (rc = place(k - 1)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
+        if ((rc = place(k)) != SLZW_RC_OK) return fail(rc);
+        if (k + kPipe < chunks && (rc = enqueue(k + kPipe)) != SLZW_RC_OK) return fail(rc);
     }
-    if ((rc = place(chunks - 1)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
-    for (int i = 0; i < kPipe; i++) CK(cudaStreamSynchronize(ctx->pipe[i].stream), "cudaStreamSynchronize");
+    CKP(cudaStreamSynchronize(ep.dense), "cudaStreamSynchronize");
+    CKP(cudaStreamSynchronize(ep.cmp[0]), "cudaStreamSynchronize");
+    CKP(cudaStreamSynchronize(ep.cmp[1]), "cudaStreamSynchronize");
+#undef CKP
+    if (trace) {
+        const double t_end = host_ms();
+        fprintf(stderr, "slzw trace: encode call %.2f ms on the host clock, %zu chunks\n", t_end, chunks);
+        for (size_t k = 0; k < chunks; k++) {
+            float t[4] = {0, 0, 0, 0};
+            for (int j = 1; j < 4; j++) cudaEventElapsedTime(&t[j], tev[chunks * 4], tev[k * 4 + j]);
+            fprintf(stderr, "slzw trace: chunk %zu %7.1f MiB: enqueued %6.2f | input in %6.2f, kernels done %6.2f | placed %6.2f, copied back %6.2f\n",
+                    k, (double)(in_off[cb[k + 1]] - in_off[cb[k]]) / 1048576.0, t_enq[k], t[1], t[2],
+                    t_placed[k], t[3]);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     if (needed) *needed = hbase;
     if (deferred) ctx->deferred_total = hbase;
     if (overflow) {
@@ -791,6 +953,18 @@ int slzw_create(int device, slzw_ctx** out) {
     }
     if (const char* e = getenv("SLZW_DEC_CONFIG")) decode_select_config(atoi(e));  // tuning knob
     if (const char* e = getenv("SLZW_HOST_ZERO_COPY")) ctx->zero_copy_in = atoi(e);
+    if (const char* e = getenv("SLZW_HOST_ENC_HILL")) {  // tuning knob: "first_mb:second:grow:taper[:peak_mb]"
+        double a, b, c, d, pk = 0;
+        const int k = sscanf(e, "%lf:%lf:%lf:%lf:%lf", &a, &b, &c, &d, &pk);
+        if (k >= 4 && a > 0 && b >= 1 && c > 1 && d > 0 && d < 1) {
+            ctx->enc_shape = 1;
+            ctx->hill.first_mb = a;
+            ctx->hill.second = b;
+            ctx->hill.grow = c;
+            ctx->hill.taper = d;
+            if (k == 5 && pk >= 1) ctx->enc_chunk_bytes = (uint64_t)(pk * 1048576.0);
+        }
+    }
     if (const char* e = getenv("SLZW_HOST_CHUNK_BYTES")) {
         const long long v = atoll(e);  // tests use tiny chunks
         if (v > 0) {
@@ -830,6 +1004,7 @@ void slzw_destroy(slzw_ctx* ctx) {
             if (w.done) cudaEventDestroy(w.done);
         }
         for (int i = 0; i < kPipe; i++) ctx->pipe[i].release();
+        ctx->enc_pipe.release();
         ctx->shard_dense.release();
     }
     delete ctx;
