@@ -525,16 +525,20 @@ __device__ __forceinline__ void match_tile_lat(uint32_t* __restrict__ table, con
 // aligned word at p - skew + 4 * lane, or 0 when it holds no byte of [p, p + tile_len).  A word
 // that lies partly outside the tile is assembled from byte loads, so nothing outside
 // [p, p + tile_len) is ever touched (the input may be pinned host memory read in place).
+// The loads go to L2 (ld.global.cg): every byte is read once, and in a streaming launch
+// (StreamCtl) the bytes behind a window boundary are written by the copy engine while the kernel
+// runs -- a 32-byte sector that straddles the boundary must not be served from an L1 line that
+// was filled before they arrived.
 __device__ __forceinline__ uint32_t load_tile_word(const uint8_t* __restrict__ p, uint32_t skew,
                                                    uint32_t tile_len, int lane) {
     const uint32_t lo = 4u * (uint32_t)lane;
     const uint32_t end = skew + tile_len;
-    if (lo >= skew && lo + 4u <= end) return __ldg(reinterpret_cast<const uint32_t*>(p - skew + lo));
+    if (lo >= skew && lo + 4u <= end) return __ldcg(reinterpret_cast<const uint32_t*>(p - skew + lo));
     uint32_t v = 0u;
     if (lo + 3u >= skew && lo < end) {
 #pragma unroll
         for (uint32_t b = 0; b < 4u; b++)
-            if (lo + b >= skew && lo + b < end) v |= (uint32_t)__ldg(p - skew + lo + b) << (8u * b);
+            if (lo + b >= skew && lo + b < end) v |= (uint32_t)__ldcg(p - skew + lo + b) << (8u * b);
     }
     return v;
 }
@@ -675,12 +679,12 @@ __device__ void encode_stream(const DevBatch& a, uint32_t sid, uint32_t* __restr
 
     if (!FIXED) push(clear_code, m.ws);  // encoder.rs:297
     if (n > 0) {
-        const uint32_t first = __ldg(src);  // encoder.rs:311 / 637: not range-checked
+        const uint32_t first = __ldcg(src);  // encoder.rs:311 / 637: not range-checked
         m.t = scrq<true>(first) << 20;
         if (!FIXED && n > 1 && first >= first_code) {
             // find_word would index past tree.nodes (encoder.rs:99) unless the second byte
             // is rejected first (encoder.rs:315-317)
-            const uint32_t k = __ldg(src + 1);
+            const uint32_t k = __ldcg(src + 1);
             if (k > max_code) {
                 status = SLZW_ERR_UNEXPECTED_CODE;
                 detail = k;
@@ -908,7 +912,42 @@ slzw_encode_kernel(const DevBatch a, const uint32_t dyn_bytes) {
         q = __shfl_sync(kFullMask, q, 0);
         if (q >= a.n) break;
         const uint32_t sid = a.order ? a.order[q] : (uint32_t)q;
-        encode_stream<TILE, FIXED, (TWARPS > 0), U, LAT>(a, sid, table, tb, tmem_warp, S, lane);
+        uint32_t win = 0;
+        bool arrived = true;
+        if (a.sc.win_of) {  // streaming launch: wait for the window of this stream
+            win = a.sc.win_of[q];
+            const long long t0 = clock64();
+            for (;;) {
+                uint32_t v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(a.sc.avail) : "memory");
+                if (v > win) break;
+                __nanosleep(500);
+                if (clock64() - t0 > (16ll << 30)) {  // about 9 s: the copy never came
+                    arrived = false;
+                    break;
+                }
+            }
+        }
+        if (arrived) {
+            encode_stream<TILE, FIXED, (TWARPS > 0), U, LAT>(a, sid, table, tb, tmem_warp, S, lane);
+        } else if (lane == 0) {
+            a.out_len[sid] = 0;
+            a.status[sid] = SLZW_ERR_IO_UNEXPECTED_EOF;
+            a.detail[sid] = 0;
+            *a.sc.host_abort = 1u;
+        }
+        if (a.sc.win_of) {
+            // everything this warp wrote for the stream is visible before the stream counts as done
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t before = atomicAdd(&a.sc.done[win], 1u);
+                if (before + 1u == a.sc.win_count[win]) {
+                    __threadfence_system();
+                    a.sc.host_flags[win] = 1u;
+                }
+            }
+        }
     }
 
     if constexpr (TWARPS > 0) {

@@ -9,10 +9,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <new>
 #include <chrono>
+#include <thread>
 #include <vector>
 
 #include "slzw_device.cuh"
@@ -92,7 +94,7 @@ constexpr int kPipe = 4;
 // of its longest stream), at most kMaxChunks per call
 // measured on config 3 (profiles/r01_e2e_notes.md): the encoder wants larger chunks (every chunk
 // pays the tail of its longest streams at 28 streams per SM), the decoder is copy-bound
-constexpr uint64_t kEncChunkBytes = 384ull << 20;
+constexpr uint64_t kEncChunkBytes = 320ull << 20;
 constexpr uint64_t kDecChunkBytes = 128ull << 20;
 constexpr uint64_t kMaxChunks = 32;
 
@@ -164,12 +166,46 @@ struct EncPipe {
     }
 };
 
+// Buffers of the streaming dense encode (run_host_encode_stream): the whole call's input, slots and
+// dense output on the device, its small arrays, the pinned staging of those, and the window flags
+// the kernel raises in mapped host memory.
+constexpr int kStreamRing = 8;  // windows whose compaction may be in flight ahead of the one being placed
+struct StreamBufs {
+    DevBuf in, slots, dense, in_off, out_off, out_len, status, detail, cs, order, win_of, win_count, ctl, dense_off;
+    PinBuf meta, flags;
+    cudaEvent_t ev_meta = nullptr, ev_cmp[kStreamRing] = {}, ev_small[kStreamRing] = {};
+    cudaError_t create_events() {
+        if (ev_meta) return cudaSuccess;
+        cudaError_t e;
+        if ((e = cudaEventCreateWithFlags(&ev_meta, cudaEventDisableTiming)) != cudaSuccess) return e;
+        for (int i = 0; i < kStreamRing; i++) {
+            if ((e = cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&ev_small[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    void release() {
+        for (DevBuf* b : {&in, &slots, &dense, &in_off, &out_off, &out_len, &status, &detail, &cs, &order, &win_of,
+                          &win_count, &ctl, &dense_off})
+            b->release();
+        meta.release();
+        flags.release();
+        if (ev_meta) cudaEventDestroy(ev_meta);
+        ev_meta = nullptr;
+        for (int i = 0; i < kStreamRing; i++) {
+            if (ev_cmp[i]) cudaEventDestroy(ev_cmp[i]);
+            if (ev_small[i]) cudaEventDestroy(ev_small[i]);
+            ev_cmp[i] = ev_small[i] = nullptr;
+        }
+    }
+};
+
 }  // namespace
 
 // ChunkShape::kHill (below): first chunk in MiB, ratio of the second to the first, growth of the
 // following ones up to the chunk size, taper after it
 struct HillShape {
-    double first_mb = 96, second = 2.0, grow = 1.36, taper = 0.62;
+    double first_mb = 80, second = 1.5, grow = 1.5, taper = 0.7;
 };
 
 struct slzw_ctx {
@@ -182,12 +218,17 @@ struct slzw_ctx {
     // overlap (PCIe is full duplex)
     HostSlot pipe[kPipe];
     EncPipe enc_pipe;  // streams and events of the dense encode pipeline
+    StreamBufs sb;     // streaming dense encode
+    int enc_stream = 1;                       // dense encode of host batches: 1 streaming, 0 chunked (SLZW_HOST_ENC_STREAM)
+    uint64_t stream_window_bytes = 64ull << 20;  // SLZW_HOST_WINDOW_MB
+    uint64_t stream_max_bytes = 12ull << 30;  // larger calls take the chunked pipeline
+    int stream_reserved_sms = 8;              // SMs the streaming encode launch leaves to the compactions (SLZW_HOST_STREAM_SMS)
     // pinned encoder input read in place by the kernels instead of staged (SLZW_HOST_ZERO_COPY): 0
     // never; 1 (default) the first chunk of a call only -- the one chunk whose staging copy nothing
     // hides; the kernels read host memory at 23 GB/s, the copy engine stages it at 55 GB/s
     // (profiles/r02_e2e_notes.md); 2 every chunk
     int zero_copy_in = 1;
-    int enc_shape = 0;  // 0 taper, 1 hill (SLZW_HOST_ENC_HILL="first_mb:second:grow:taper")
+    int enc_shape = 1;  // dense encode: 0 taper, 1 hill (SLZW_HOST_ENC_HILL="first_mb:second:grow:taper[:peak_mb]", "taper")
     HillShape hill;
     bool chunk_min_streams = true;  // off when SLZW_HOST_CHUNK_BYTES is set (tests force tiny chunks)
     uint64_t enc_chunk_bytes = kEncChunkBytes;
@@ -309,6 +350,7 @@ DevBatch make_dev_batch(const slzw_params* params, const slzw_batch* b, const Wo
     a.dec_tables = (uint32_t*)w->tables.p;
     a.enc_tables = nullptr;
     a.p = *params;
+    a.sc = StreamCtl{};
     return a;
 }
 
@@ -501,6 +543,49 @@ struct ChunkStage {
     }
 };
 
+// SLZW_HOST_TRACE=1 (debugging aid): timeline of a host-pipeline call, one line per chunk on stderr:
+// host clock when the chunk was enqueued / placed, device clock (relative to the call's first
+// event) when its input was in, its kernels were done and its output was copied back.  Every event
+// is recorded right behind an operation of its own stream (an event in front of the first copy of
+// a stream queues behind whatever the stream's last engine is doing and would delay the copy).
+struct HostTrace {
+    bool on = false;
+    size_t chunks = 0;
+    std::vector<cudaEvent_t> ev;
+    std::vector<double> t_enq, t_placed;
+    std::chrono::steady_clock::time_point t0;
+    void begin(size_t n_chunks, cudaStream_t first) {
+        on = getenv("SLZW_HOST_TRACE") != nullptr;
+        t0 = std::chrono::steady_clock::now();
+        if (!on) return;
+        chunks = n_chunks;
+        ev.resize(chunks * 3 + 1);
+        for (auto& e : ev) cudaEventCreate(&e);
+        t_enq.assign(chunks, 0.0);
+        t_placed.assign(chunks, 0.0);
+        cudaEventRecord(ev[chunks * 3], first);
+    }
+    double host_ms() const {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    void enqueued(size_t k) { if (on) t_enq[k] = host_ms(); }
+    void placed(size_t k) { if (on) t_placed[k] = host_ms(); }
+    void mark(size_t k, int what, cudaStream_t st) { if (on) cudaEventRecord(ev[k * 3 + what], st); }
+    void report(const char* call, const uint64_t* weight, const std::vector<uint64_t>& cb) {
+        if (!on) return;
+        fprintf(stderr, "slzw trace: %s call %.2f ms on the host clock, %zu chunks\n", call, host_ms(), chunks);
+        for (size_t k = 0; k < chunks; k++) {
+            float t[3] = {0, 0, 0};
+            for (int j = 0; j < 3; j++) cudaEventElapsedTime(&t[j], ev[chunks * 3], ev[k * 3 + j]);
+            fprintf(stderr, "slzw trace: chunk %zu %7.1f MiB: enqueued %6.2f | input in %6.2f, kernels done %6.2f | placed %6.2f, copied back %6.2f\n",
+                    k, (double)(weight[cb[k + 1]] - weight[cb[k]]) / 1048576.0, t_enq[k], t[0], t[1], t_placed[k], t[2]);
+        }
+    }
+    ~HostTrace() {
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
+};
+
 // An error in the middle of a pipelined call: copies of earlier chunks into the caller's buffers may
 // still be in flight, so the slots are drained before the call returns (the error text is kept).
 int drain_pipe(slzw_ctx* ctx, int rc) {
@@ -545,6 +630,8 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
     const uint8_t* in_alias =
         (op == Op::Encode && ctx->zero_copy_in > 0 && !predict) ? device_alias(b->in) : nullptr;
 
+    HostTrace tr;
+    tr.begin(chunks, ctx->pipe[0].stream);
     const uint8_t* const in_alias_call = in_alias;
     auto enqueue = [&](size_t k) -> int {
         HostSlot& hs = ctx->pipe[k % kPipe];
@@ -570,6 +657,7 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
         memcpy(st.in_off, b->in_off + s0, sizeof(uint64_t) * (m + 1));
         if (needs_out) memcpy(st.out_off, b->out_off + s0, sizeof(uint64_t) * (m + 1));
         if (b->code_size) memcpy(st.cs, b->code_size + s0, m);
+        tr.enqueued(k);
         // Offsets stay absolute: the device copies of in/out are biased by -lo instead.
         if (!in_alias && in_hi > in_lo)
             CK(cudaMemcpyAsync(hs.in.p, b->in + in_lo, in_hi - in_lo, cudaMemcpyHostToDevice, s), "H2D in");
@@ -579,6 +667,7 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
             CK(cudaMemcpyAsync(hs.out_off.p, st.out_off, sizeof(uint64_t) * (m + 1), cudaMemcpyHostToDevice, s),
                "H2D out_off");
         if (b->code_size) CK(cudaMemcpyAsync(hs.cs.p, st.cs, m, cudaMemcpyHostToDevice, s), "H2D code_size");
+        tr.mark(k, 0, s);
         slzw_batch d = {};
         d.in = in_alias ? in_alias : (const uint8_t*)hs.in.p - in_lo;
         d.in_off = (const uint64_t*)hs.in_off.p;
@@ -601,8 +690,10 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
                                 ctx->num_sms, s), "predictor launch");
             ctx->launches += 1;
         }
+        tr.mark(k, 1, s);
         if (needs_out && out_hi > out_lo)
             CK(cudaMemcpyAsync(b->out + out_lo, hs.out.p, out_hi - out_lo, cudaMemcpyDeviceToHost, s), "D2H out");
+        tr.mark(k, 2, s);
         CK(cudaMemcpyAsync(st.out_len, hs.out_len.p, sizeof(uint64_t) * m, cudaMemcpyDeviceToHost, s), "D2H out_len");
         CK(cudaMemcpyAsync(st.status, hs.status.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H status");
         CK(cudaMemcpyAsync(st.detail, hs.detail.p, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost, s), "D2H detail");
@@ -617,6 +708,7 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
         memcpy(b->out_len + s0, st.out_len, sizeof(uint64_t) * m);
         memcpy(b->status + s0, st.status, sizeof(uint32_t) * m);
         memcpy(b->detail + s0, st.detail, sizeof(uint32_t) * m);
+        tr.placed(k);
         return SLZW_RC_OK;
     };
 
@@ -628,6 +720,298 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
     }
     for (size_t k = chunks >= (size_t)kPipe ? chunks - kPipe + 1 : 0; k < chunks; k++)
         if ((rc = finalize(k)) != SLZW_RC_OK) return drain_pipe(ctx, rc);
+    tr.report(op == Op::Encode ? "encode" : "decode", needs_out && op == Op::Decode ? b->out_off : b->in_off, cb);
+    return SLZW_RC_OK;
+}
+
+// Streaming dense encode of a host batch: ONE encode launch for the whole call.
+//
+// The chunked pipeline below pays for its chunk boundaries: an encode CTA owns its SM until its 28
+// warps are done, a warp whose chunk has run dry cannot take a stream of the next chunk, so a chunk
+// that gives every warp only a stream or two leaves half of the dictionaries idle (the first and
+// the last chunks of a call, which have to be small: 25 ms for the first 0.38 GB of config 3), and
+// the compaction of a chunk cannot run before the encode kernel behind it drains.  Here the input
+// is cut into windows (16, 32, then 64 MiB) that the copy engine delivers back to back, each
+// followed by a 4-byte copy that advances a device word (`avail`); the kernel's warps take streams
+// from one queue over all windows -- largest first inside a window -- and wait for `avail` only when
+// they have caught up with the copies (StreamCtl, slzw_device.cuh).  The launch leaves
+// stream_reserved_sms SMs free; the warp that finishes a window's last stream raises the window's
+// flag in mapped host memory, and the host starts that window's compaction (on the free SMs),
+// reads its sizes back, places it behind the previous window and copies it out.
+int run_host_encode_stream(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
+                           const uint64_t* in_off, uint64_t n, const uint8_t* code_size, uint64_t align,
+                           uint8_t* out_dense, uint64_t out_cap, uint64_t* out_off, uint32_t* status,
+                           uint32_t* detail, uint64_t* needed) {
+    NvtxRange range("slzw encode batch, dense (streaming host pipeline)");
+    EncPipe& ep = ctx->enc_pipe;
+    StreamBufs& sb = ctx->sb;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        CK(ep.create(), "cudaStreamCreate / cudaEventCreate (encode pipeline)");
+        CK(sb.create_events(), "cudaEventCreate (streaming encode)");
+    }
+    const uint64_t in_lo = in_off[0], total = in_off[n] - in_off[0];
+    // ---- windows: stream ranges [wb[w], wb[w + 1]) ----
+    std::vector<uint64_t> wb;
+    {
+        uint64_t target = ctx->chunk_min_streams ? ctx->stream_window_bytes : ctx->enc_chunk_bytes;
+        if (target < 1) target = 1;
+        while (total / target > 4000) target *= 2;  // window indices are 16 bits
+        uint64_t size = ctx->chunk_min_streams && target > (16ull << 20) ? (16ull << 20) : target;
+        wb.push_back(0);
+        uint64_t i = 0;
+        while (i < n) {
+            const uint64_t end = in_off[i] + size;
+            uint64_t j = i + 1;
+            while (j < n && in_off[j + 1] <= end) j++;
+            wb.push_back(j);
+            i = j;
+            size = size * 2 < target ? size * 2 : target;
+        }
+    }
+    const size_t W = wb.size() - 1;
+    // ---- buffers ----
+    const size_t ctl_bytes = 128 + 4 * W;
+    auto up8 = [](size_t v) { return (v + 7) & ~size_t(7); };
+    const size_t meta_bytes = up8(8 * (n + 1)) * 2 + up8(4 * n) + up8(2 * n) + up8(4 * W) * 2 + up8(ctl_bytes) + up8(n) +
+                              up8(8 * (n + W)) + up8(4 * n) * 2 + 64;
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        CK(sb.meta.reserve(meta_bytes), "cudaHostAlloc(meta)");
+        CK(sb.flags.reserve(4 * (W + 1)), "cudaHostAlloc(flags)");
+        CK(sb.in.reserve(total + 16), "cudaMalloc(in)");
+        CK(sb.in_off.reserve(8 * (n + 1)), "cudaMalloc(in_off)");
+        CK(sb.out_off.reserve(8 * (n + 1)), "cudaMalloc(out_off)");
+        CK(sb.out_len.reserve(8 * n), "cudaMalloc(out_len)");
+        CK(sb.status.reserve(4 * n), "cudaMalloc(status)");
+        CK(sb.detail.reserve(4 * n), "cudaMalloc(detail)");
+        CK(sb.order.reserve(4 * n), "cudaMalloc(order)");
+        CK(sb.win_of.reserve(2 * n), "cudaMalloc(win_of)");
+        CK(sb.win_count.reserve(4 * W), "cudaMalloc(win_count)");
+        CK(sb.ctl.reserve(ctl_bytes), "cudaMalloc(ctl)");
+        CK(sb.dense_off.reserve(8 * (n + W)), "cudaMalloc(dense_off)");
+        if (code_size) CK(sb.cs.reserve(n), "cudaMalloc(code_size)");
+    }
+    uint8_t* mp = (uint8_t*)sb.meta.p;
+    auto carve = [&](size_t bytes) {
+        uint8_t* r = mp;
+        mp += up8(bytes);
+        return r;
+    };
+    uint64_t* h_in_off = (uint64_t*)carve(8 * (n + 1));
+    uint64_t* h_slots = (uint64_t*)carve(8 * (n + 1));
+    uint32_t* h_order = (uint32_t*)carve(4 * n);
+    uint16_t* h_win_of = (uint16_t*)carve(2 * n);
+    uint32_t* h_win_count = (uint32_t*)carve(4 * W);
+    uint32_t* h_avail = (uint32_t*)carve(4 * W);
+    uint8_t* h_zero = carve(ctl_bytes);
+    uint8_t* h_cs = carve(n);
+    uint64_t* h_dense_off = (uint64_t*)carve(8 * (n + W));
+    uint32_t* h_status = (uint32_t*)carve(4 * n);
+    uint32_t* h_detail = (uint32_t*)carve(4 * n);
+    volatile uint32_t* h_flags = (volatile uint32_t*)sb.flags.p;
+    uint32_t* d_flags = nullptr;
+    CK(cudaHostGetDevicePointer((void**)&d_flags, sb.flags.p, 0), "cudaHostGetDevicePointer");
+    for (size_t w = 0; w <= W; w++) h_flags[w] = 0;
+    memset(h_zero, 0, ctl_bytes);
+    for (size_t w = 0; w < W; w++) h_avail[w] = (uint32_t)(w + 1);
+    unsigned long long* d_queue = (unsigned long long*)sb.ctl.p;
+    uint32_t* d_avail = (uint32_t*)((uint8_t*)sb.ctl.p + 64);
+    uint32_t* d_done = (uint32_t*)((uint8_t*)sb.ctl.p + 128);
+
+    HostTrace tr;
+    tr.begin(W, ep.in);
+    auto fail = [&](int rc) {
+        // the kernel may still be waiting for input that will not come: it gives up by itself
+        ep.sync_all();
+        cudaGetLastError();
+        return rc;
+    };
+#define CKS(call, what)                                               \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) return fail(fail_cuda(ctx, e_, what)); \
+    } while (0)
+    // ---- input copies, each followed by the word that tells the kernel the window is in ----
+    CKS(cudaMemcpyAsync(sb.ctl.p, h_zero, ctl_bytes, cudaMemcpyHostToDevice, ep.in), "H2D ctl");
+    auto copy_window = [&](size_t w) -> int {
+        const uint64_t lo = in_off[wb[w]], hi = in_off[wb[w + 1]];
+        tr.enqueued(w);
+        if (hi > lo)
+            CK(cudaMemcpyAsync((uint8_t*)sb.in.p + (lo - in_lo), in + lo, hi - lo, cudaMemcpyHostToDevice, ep.in), "H2D in");
+        CK(cudaMemcpyAsync(d_avail, h_avail + w, 4, cudaMemcpyHostToDevice, ep.in), "H2D avail");
+        tr.mark(w, 0, ep.in);
+        return SLZW_RC_OK;
+    };
+    int rc;
+    const size_t early = W < 2 ? W : 2;  // these copies run while the host prepares the small arrays
+    for (size_t w = 0; w < early; w++)
+        if ((rc = copy_window(w)) != SLZW_RC_OK) return fail(rc);
+    // ---- small arrays: offsets, worst-case slots, processing order (window by window, largest
+    // streams first inside a window: counting sort over 1/8-octave size classes) ----
+    memcpy(h_in_off, in_off, 8 * (n + 1));
+    if (code_size) memcpy(h_cs, code_size, n);
+    h_slots[0] = 0;
+    {
+        constexpr int kClasses = 64 * 8 + 1;
+        std::vector<uint32_t> count(kClasses);
+        std::vector<uint16_t> cls(n);
+        for (size_t w = 0; w < W; w++) {
+            const uint64_t s0 = wb[w], s1 = wb[w + 1];
+            h_win_count[w] = (uint32_t)(s1 - s0);
+            std::fill(count.begin(), count.end(), 0u);
+            for (uint64_t i = s0; i < s1; i++) {
+                const uint64_t len = in_off[i + 1] - in_off[i];
+                h_slots[i + 1] = h_slots[i] + ((slzw_encode_bound(params, len) + 15) & ~15ull);
+                int c = 0;
+                if (len) {
+                    const int msb = 63 - __builtin_clzll(len);
+                    c = 1 + msb * 8 + (int)(msb >= 3 ? (len >> (msb - 3)) & 7 : (len << (3 - msb)) & 7);
+                }
+                cls[i] = (uint16_t)c;
+                count[c]++;
+            }
+            // descending classes: start[c] = number of streams in larger classes
+            uint32_t acc = 0;
+            for (int c = kClasses - 1; c >= 0; c--) {
+                const uint32_t k = count[c];
+                count[c] = acc;
+                acc += k;
+            }
+            for (uint64_t i = s0; i < s1; i++) {
+                const uint64_t q = s0 + count[cls[i]]++;
+                h_order[q] = (uint32_t)i;
+                h_win_of[q] = (uint16_t)w;
+            }
+        }
+    }
+    const uint64_t slot_bytes = h_slots[n];
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        CKS(sb.slots.reserve(slot_bytes + 16), "cudaMalloc(slots)");
+        CKS(sb.dense.reserve(slot_bytes + align * n + 256), "cudaMalloc(dense)");
+    }
+    CKS(cudaMemcpyAsync(sb.in_off.p, h_in_off, 8 * (n + 1), cudaMemcpyHostToDevice, ep.in), "H2D in_off");
+    CKS(cudaMemcpyAsync(sb.out_off.p, h_slots, 8 * (n + 1), cudaMemcpyHostToDevice, ep.in), "H2D slots");
+    CKS(cudaMemcpyAsync(sb.order.p, h_order, 4 * n, cudaMemcpyHostToDevice, ep.in), "H2D order");
+    CKS(cudaMemcpyAsync(sb.win_of.p, h_win_of, 2 * n, cudaMemcpyHostToDevice, ep.in), "H2D win_of");
+    CKS(cudaMemcpyAsync(sb.win_count.p, h_win_count, 4 * W, cudaMemcpyHostToDevice, ep.in), "H2D win_count");
+    if (code_size) CKS(cudaMemcpyAsync(sb.cs.p, h_cs, n, cudaMemcpyHostToDevice, ep.in), "H2D code_size");
+    CKS(cudaEventRecord(sb.ev_meta, ep.in), "cudaEventRecord");
+    for (size_t w = early; w < W; w++)
+        if ((rc = copy_window(w)) != SLZW_RC_OK) return fail(rc);
+    // ---- the one encode launch ----
+    {
+        std::lock_guard<std::mutex> lock(ctx->mu);
+        DevBatch a;
+        a.in = (const uint8_t*)sb.in.p - in_lo;
+        a.in_off = (const uint64_t*)sb.in_off.p;
+        a.out = (uint8_t*)sb.slots.p;
+        a.out_off = (const uint64_t*)sb.out_off.p;
+        a.out_len = (uint64_t*)sb.out_len.p;
+        a.status = (uint32_t*)sb.status.p;
+        a.detail = (uint32_t*)sb.detail.p;
+        a.code_size = code_size ? (const uint8_t*)sb.cs.p : nullptr;
+        a.n = n;
+        a.order = (const uint32_t*)sb.order.p;
+        a.queue = d_queue;
+        a.retry = nullptr;
+        a.retry_ids = nullptr;
+        a.n_dev = nullptr;
+        a.dec_tables = nullptr;
+        a.enc_tables = nullptr;
+        a.p = *params;
+        a.sc.win_of = (const uint16_t*)sb.win_of.p;
+        a.sc.win_count = (const uint32_t*)sb.win_count.p;
+        a.sc.done = d_done;
+        a.sc.avail = d_avail;
+        a.sc.host_flags = d_flags;
+        a.sc.host_abort = d_flags + W;
+        CKS(cudaStreamWaitEvent(ep.cmp[0], sb.ev_meta, 0), "cudaStreamWaitEvent");
+        int sms = ctx->num_sms - ctx->stream_reserved_sms;
+        if (sms < 1) sms = 1;
+        CKS(encode_launch(a, sms, ep.cmp[0]), "encode launch");
+        ctx->launches += 1;
+        ctx->last_encode_ws = -1;
+    }
+    // ---- windows come back: compaction as soon as the kernel raises the flag, placement in order ----
+    uint64_t hbase = 0;
+    bool overflow = false;
+    size_t launched = 0, placed = 0;
+    // worst-case position of a window in the device dense buffer
+    auto dense_base = [&](size_t w) { return h_slots[wb[w]] + align * wb[w]; };
+    const auto t_wait0 = std::chrono::steady_clock::now();
+    auto waited_s = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_wait0).count(); };
+    double last_progress = 0.0;
+    while (placed < W) {
+        bool progress = false;
+        while (launched < W && launched < placed + kStreamRing && h_flags[launched] != 0) {
+            const size_t w = launched;
+            const int r = (int)(w % kStreamRing);
+            const uint64_t s0 = wb[w], m = wb[w + 1] - wb[w];
+            uint64_t* d_doff = (uint64_t*)sb.dense_off.p + s0 + w;
+            CKS(compact_launch((const uint8_t*)sb.slots.p, (const uint64_t*)sb.out_off.p + s0,
+                               (const uint64_t*)sb.out_len.p + s0, m, align, (uint8_t*)sb.dense.p + dense_base(w),
+                               d_doff, ctx->num_sms, ep.cmp[1]), "compaction launch");
+            ctx->launches += 2;
+            CKS(cudaEventRecord(sb.ev_cmp[r], ep.cmp[1]), "cudaEventRecord");
+            tr.mark(w, 1, ep.cmp[1]);
+            CKS(cudaStreamWaitEvent(ep.small, sb.ev_cmp[r], 0), "cudaStreamWaitEvent");
+            CKS(cudaMemcpyAsync(h_dense_off + s0 + w, d_doff, 8 * (m + 1), cudaMemcpyDeviceToHost, ep.small), "D2H dense_off");
+            CKS(cudaMemcpyAsync(h_status + s0, (uint32_t*)sb.status.p + s0, 4 * m, cudaMemcpyDeviceToHost, ep.small), "D2H status");
+            CKS(cudaMemcpyAsync(h_detail + s0, (uint32_t*)sb.detail.p + s0, 4 * m, cudaMemcpyDeviceToHost, ep.small), "D2H detail");
+            CKS(cudaEventRecord(sb.ev_small[r], ep.small), "cudaEventRecord");
+            launched++;
+            progress = true;
+        }
+        if (placed < launched) {
+            const cudaError_t q = cudaEventQuery(sb.ev_small[placed % kStreamRing]);
+            if (q == cudaSuccess) {
+                const size_t w = placed;
+                const uint64_t s0 = wb[w], m = wb[w + 1] - wb[w];
+                const uint64_t* doff = h_dense_off + s0 + w;
+                const uint64_t tot = doff[m];
+                for (uint64_t i = 1; i <= m; i++) out_off[s0 + i] = hbase + doff[i];
+                memcpy(status + s0, h_status + s0, 4 * m);
+                memcpy(detail + s0, h_detail + s0, 4 * m);
+                if (hbase + tot > out_cap) overflow = true;
+                if (!overflow && tot)
+                    CKS(cudaMemcpyAsync(out_dense + hbase, (uint8_t*)sb.dense.p + dense_base(w), tot,
+                                        cudaMemcpyDeviceToHost, ep.dense), "D2H dense");
+                tr.placed(w);
+                tr.mark(w, 2, ep.dense);
+                hbase += tot;
+                placed++;
+                progress = true;
+            } else if (q != cudaErrorNotReady) {
+                return fail(fail_cuda(ctx, q, "cudaEventQuery"));
+            }
+        }
+        if (progress) {
+            last_progress = waited_s();
+        } else {
+            if (h_flags[W] != 0 || waited_s() - last_progress > 30.0) {
+                snprintf(ctx->err, sizeof ctx->err, "streaming encode stalled (window %zu of %zu)", placed, W);
+                return fail(SLZW_RC_CUDA);
+            }
+            std::this_thread::yield();
+        }
+    }
+    CKS(cudaStreamSynchronize(ep.dense), "cudaStreamSynchronize");
+    CKS(cudaStreamSynchronize(ep.cmp[0]), "cudaStreamSynchronize");
+    CKS(cudaStreamSynchronize(ep.cmp[1]), "cudaStreamSynchronize");
+#undef CKS
+    if (h_flags[W] != 0) {
+        snprintf(ctx->err, sizeof ctx->err, "streaming encode: a window's input did not arrive");
+        return SLZW_RC_CUDA;
+    }
+    tr.report("encode (dense, streaming)", in_off, wb);
+    if (needed) *needed = hbase;
+    if (overflow) {
+        snprintf(ctx->err, sizeof ctx->err, "dense output needs %llu bytes, capacity is %llu",
+                 (unsigned long long)hbase, (unsigned long long)out_cap);
+        return SLZW_RC_NOMEM;
+    }
     return SLZW_RC_OK;
 }
 
@@ -671,6 +1055,12 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     NvtxRange range("slzw encode batch, dense (host pipeline)");
     DeviceGuard guard(ctx->device);
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
+    // one launch over the whole call when its buffers fit comfortably (4.2 x the input) and nothing
+    // has to touch the input on the device first
+    if (ctx->enc_stream && !deferred && ctx->pred_row_bytes == 0 && n <= 0xFFFFFFFFull &&
+        in_off[n] - in_off[0] <= ctx->stream_max_bytes)
+        return run_host_encode_stream(ctx, params, in, in_off, n, code_size, align, out_dense, out_cap, out_off,
+                                      status, detail, needed);
     EncPipe& ep = ctx->enc_pipe;
     {
         std::lock_guard<std::mutex> lock(ctx->mu);
@@ -700,27 +1090,10 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
         CK(ctx->shard_dense.reserve(dev_off[chunks] + 256), "cudaMalloc(dense shard)");
     }
 
-    // SLZW_HOST_TRACE=1 (debugging aid): timeline of the call, one line per chunk on stderr.
-    // Every event is recorded right behind an operation of its own stream (an event in front of
-    // the first copy of a stream queues behind whatever the stream's last engine is doing).
-    const bool trace = getenv("SLZW_HOST_TRACE") != nullptr;
-    std::vector<cudaEvent_t> tev;
-    std::vector<double> t_enq(chunks, 0.0), t_placed(chunks, 0.0);
-    const auto t_call = std::chrono::steady_clock::now();
-    auto host_ms = [&]() {
-        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count();
-    };
-    if (trace) {
-        tev.resize(chunks * 4 + 1);
-        for (auto& e : tev) cudaEventCreate(&e);
-        cudaEventRecord(tev[chunks * 4], ep.in);
-    }
-    auto mark = [&](size_t k, int what, cudaStream_t st) {
-        if (trace) cudaEventRecord(tev[k * 4 + what], st);
-    };
+    HostTrace tr;
+    tr.begin(chunks, ep.in);
     auto fail = [&](int rc) {
         ep.sync_all();
-        for (auto& e : tev) cudaEventDestroy(e);
         return drain_pipe(ctx, rc);
     };
 #define CKP(call, what)                                             \
@@ -764,7 +1137,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
             CK(hs.detail.reserve(sizeof(uint32_t) * m), "cudaMalloc(detail)");
             if (code_size) CK(hs.cs.reserve(m), "cudaMalloc(code_size)");
         }
-        if (trace) t_enq[k] = host_ms();
+        tr.enqueued(k);
         // input: the slot's previous chunk (k - kPipe) was placed before this call, so its kernels
         // are done with these buffers
         if (!in_alias && in_hi > in_lo)
@@ -775,7 +1148,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
            "H2D slots");
         if (code_size) CK(cudaMemcpyAsync(hs.cs.p, st.cs, m, cudaMemcpyHostToDevice, ep.in), "H2D code_size");
         CK(cudaEventRecord(ep.ev_in[slot], ep.in), "cudaEventRecord");
-        mark(k, 1, ep.in);
+        tr.mark(k, 0, ep.in);
         // kernels
         CK(cudaStreamWaitEvent(sc, ep.ev_in[slot], 0), "cudaStreamWaitEvent");
         // the dense copy of the slot's previous chunk must have left the dense buffer
@@ -802,7 +1175,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
                           (uint64_t*)hs.dense_off.p, ctx->num_sms, sc), "compaction launch");
         ctx->launches += 2;
         CK(cudaEventRecord(ep.ev_cmp[slot], sc), "cudaEventRecord");
-        mark(k, 2, sc);
+        tr.mark(k, 1, sc);
         // the chunk's dense offsets come back in the out_len area of the stage (m + 1 entries)
         CK(cudaStreamWaitEvent(ep.small, ep.ev_cmp[slot], 0), "cudaStreamWaitEvent");
         CK(cudaMemcpyAsync(st.out_len, hs.dense_off.p, sizeof(uint64_t) * (m + 1), cudaMemcpyDeviceToHost, ep.small),
@@ -834,8 +1207,8 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
                    "D2H dense");
             CK(cudaEventRecord(ep.ev_out[slot], ep.dense), "cudaEventRecord");
         }
-        if (trace) t_placed[k] = host_ms();
-        mark(k, 3, ep.dense);
+        tr.placed(k);
+        tr.mark(k, 2, ep.dense);
         hbase += total;
         return SLZW_RC_OK;
     };
@@ -852,18 +1225,7 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     CKP(cudaStreamSynchronize(ep.cmp[0]), "cudaStreamSynchronize");
     CKP(cudaStreamSynchronize(ep.cmp[1]), "cudaStreamSynchronize");
 #undef CKP
-    if (trace) {
-        const double t_end = host_ms();
-        fprintf(stderr, "slzw trace: encode call %.2f ms on the host clock, %zu chunks\n", t_end, chunks);
-        for (size_t k = 0; k < chunks; k++) {
-            float t[4] = {0, 0, 0, 0};
-            for (int j = 1; j < 4; j++) cudaEventElapsedTime(&t[j], tev[chunks * 4], tev[k * 4 + j]);
-            fprintf(stderr, "slzw trace: chunk %zu %7.1f MiB: enqueued %6.2f | input in %6.2f, kernels done %6.2f | placed %6.2f, copied back %6.2f\n",
-                    k, (double)(in_off[cb[k + 1]] - in_off[cb[k]]) / 1048576.0, t_enq[k], t[1], t[2],
-                    t_placed[k], t[3]);
-        }
-        for (auto& e : tev) cudaEventDestroy(e);
-    }
+    tr.report("encode (dense)", in_off, cb);
     if (needed) *needed = hbase;
     if (deferred) ctx->deferred_total = hbase;
     if (overflow) {
@@ -953,8 +1315,18 @@ int slzw_create(int device, slzw_ctx** out) {
     }
     if (const char* e = getenv("SLZW_DEC_CONFIG")) decode_select_config(atoi(e));  // tuning knob
     if (const char* e = getenv("SLZW_HOST_ZERO_COPY")) ctx->zero_copy_in = atoi(e);
+    if (const char* e = getenv("SLZW_HOST_ENC_STREAM")) ctx->enc_stream = atoi(e) != 0;  // tuning knobs
+    if (const char* e = getenv("SLZW_HOST_WINDOW_MB")) {
+        const double v = atof(e);
+        if (v >= 0.001) ctx->stream_window_bytes = (uint64_t)(v * 1048576.0);
+    }
+    if (const char* e = getenv("SLZW_HOST_STREAM_SMS")) {
+        const int v = atoi(e);
+        if (v >= 0 && v < prop.multiProcessorCount / 2) ctx->stream_reserved_sms = v;
+    }
     if (const char* e = getenv("SLZW_HOST_ENC_HILL")) {  // tuning knob: "first_mb:second:grow:taper[:peak_mb]"
         double a, b, c, d, pk = 0;
+        if (!strcmp(e, "taper")) ctx->enc_shape = 0;
         const int k = sscanf(e, "%lf:%lf:%lf:%lf:%lf", &a, &b, &c, &d, &pk);
         if (k >= 4 && a > 0 && b >= 1 && c > 1 && d > 0 && d < 1) {
             ctx->enc_shape = 1;
@@ -1005,6 +1377,7 @@ void slzw_destroy(slzw_ctx* ctx) {
         }
         for (int i = 0; i < kPipe; i++) ctx->pipe[i].release();
         ctx->enc_pipe.release();
+        ctx->sb.release();
         ctx->shard_dense.release();
     }
     delete ctx;

@@ -11,6 +11,21 @@ constexpr int kWarpSize = 32;
 constexpr uint32_t kFullMask = 0xffffffffu;
 
 // Device view of slzw_batch plus the schedule produced by the stream scheduler.
+// Streaming encode (host pipeline, slzw_api.cu run_host_encode_stream): ONE encode launch covers
+// the whole call while its input still arrives, window by window, over the copy engine.  Queue
+// position q belongs to window win_of[q]; a warp waits until `avail` (a device word the copy
+// stream writes behind each window's bytes) says that window is in, and the warp that finishes the
+// last stream of a window raises the window's flag in mapped host memory, on which the host starts
+// the window's compaction and copy back.  win_of == nullptr: everything is there (plain launch).
+struct StreamCtl {
+    const uint16_t* win_of;      // n entries
+    const uint32_t* win_count;   // streams per window
+    uint32_t* done;              // streams finished per window, zeroed before the launch
+    const uint32_t* avail;       // number of windows whose input has arrived
+    volatile uint32_t* host_flags;  // mapped pinned host memory, one word per window
+    volatile uint32_t* host_abort;  // mapped pinned host memory: a wait for input timed out
+};
+
 struct DevBatch {
     const uint8_t* in;
     const uint64_t* in_off;
@@ -29,6 +44,7 @@ struct DevBatch {
     uint32_t* dec_tables;           // fast decode: 16 KB table blocks of the warps without a shared-memory table
     uint8_t* enc_tables;            // encode: 16 KB dictionaries of the lanes in global memory (16 KB-aligned)
     slzw_params p;
+    StreamCtl sc;                   // encode only
 };
 
 // ---- stream staging -------------------------------------------------------------------------

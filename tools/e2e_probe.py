@@ -32,7 +32,8 @@ def main():
     p = tiff_params()
     # settings: "name=ENV1=val,ENV2=val" arguments after the stream count; default = the shipped path
     settings = [a.split("=", 1) for a in sys.argv[2:]] or [["default", ""]]
-    knobs = ("SLZW_HOST_CHUNK_BYTES", "SLZW_HOST_ZERO_COPY", "SLZW_HOST_ENC_HILL", "SLZW_HOST_DEC_HILL")
+    knobs = ("SLZW_HOST_CHUNK_BYTES", "SLZW_HOST_ZERO_COPY", "SLZW_HOST_ENC_HILL", "SLZW_HOST_ENC_STREAM",
+             "SLZW_HOST_WINDOW_MB", "SLZW_HOST_STREAM_SMS")
     for name, envs in settings:
         for k in knobs:
             os.environ.pop(k, None)
