@@ -560,10 +560,10 @@ def run_ours(args):
                "numa_node_rank0": numa_node,
                "host_link_gbs_per_direction": link,
                "frac_of_host_link": (max(h2d, d2h) * e2e_steps / dt / 1e9 / link) if link else None,
-               "note": "slzw_encode_batch_host_dense + slzw_decode_batch_host on pinned host buffers; the "
-                       "encoder reads its pinned input in place over PCIe (counted in h2d_bytes_per_step), "
-                       "everything else is cudaMemcpyAsync inside the call; host_link = pinned H2D and D2H "
-                       "copies of 1 GiB running at the same time, on all ranks at once (this rank's share)"}
+               "note": "slzw_encode_batch_host_dense + slzw_decode_batch_host on pinned host buffers; every "
+                       "byte crosses the bus by cudaMemcpyAsync inside the call (encode: one streaming launch "
+                       "fed window by window); host_link = pinned H2D and D2H copies of 1 GiB running at the "
+                       "same time, on all ranks at once (this rank's share)"}
         if pinned and world == 1 and total <= (4 << 30):
             # the same calls on pageable buffers (numpy arrays): every copy is staged by the driver
             p_dense = np.empty(dense_cap, dtype=np.uint8)

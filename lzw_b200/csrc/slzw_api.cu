@@ -220,9 +220,9 @@ struct slzw_ctx {
     EncPipe enc_pipe;  // streams and events of the dense encode pipeline
     StreamBufs sb;     // streaming dense encode
     int enc_stream = 1;                       // dense encode of host batches: 1 streaming, 0 chunked (SLZW_HOST_ENC_STREAM)
-    uint64_t stream_window_bytes = 64ull << 20;  // SLZW_HOST_WINDOW_MB
+    uint64_t stream_window_bytes = 32ull << 20;  // SLZW_HOST_WINDOW_MB
     uint64_t stream_max_bytes = 12ull << 30;  // larger calls take the chunked pipeline
-    int stream_reserved_sms = 8;              // SMs the streaming encode launch leaves to the compactions (SLZW_HOST_STREAM_SMS)
+    int stream_reserved_sms = 4;              // SMs the streaming encode launch leaves to the compactions (SLZW_HOST_STREAM_SMS)
     // pinned encoder input read in place by the kernels instead of staged (SLZW_HOST_ZERO_COPY): 0
     // never; 1 (default) the first chunk of a call only -- the one chunk whose staging copy nothing
     // hides; the kernels read host memory at 23 GB/s, the copy engine stages it at 55 GB/s

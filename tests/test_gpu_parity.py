@@ -412,11 +412,16 @@ def test_config3_scaled_down_vs_oracle(codec):
 
 
 # ---- host pipeline (chunked H2D / kernels / D2H) -----------------------------------------------
-def test_host_paths_with_many_small_chunks(monkeypatch):
-    """The host entry points split a batch into chunks of streams and pipeline them over three
-    CUDA streams; with a tiny chunk size every code path of that pipeline runs on a small batch."""
+@pytest.mark.parametrize("dense_encode", ["streaming", "chunked"])
+def test_host_paths_with_many_small_chunks(monkeypatch, dense_encode):
+    """The host entry points split a batch into chunks of streams and pipeline them over several
+    CUDA streams; with a tiny chunk size every code path of those pipelines runs on a small batch.
+    The dense encode runs once as ONE streaming launch fed window by window (the default) and once
+    through the chunked pipeline (what calls with the predictor, two-phase calls and very large
+    calls take)."""
     import lzw_b200
     monkeypatch.setenv("SLZW_HOST_CHUNK_BYTES", "20000")
+    monkeypatch.setenv("SLZW_HOST_ENC_STREAM", "1" if dense_encode == "streaming" else "0")
     c = lzw_b200.Codec(0)
     try:
         for p in (O.tiff(), O.gif(5), O.fixed(True)):
@@ -437,6 +442,50 @@ def test_host_paths_with_many_small_chunks(monkeypatch):
             o_dec, o_dlen, o_dst, o_ddet = O.decode_batch(p, d_in, d_off, off)
             assert np.array_equal(dlen, o_dlen) and np.array_equal(dst, o_dst) and np.array_equal(ddet, o_ddet)
             assert T.slots_equal(dec, o_dec, off, o_dlen) == -1
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("window_mb, reserved", [("0.03", "4"), ("0.2", "0"), ("64", "8")])
+def test_streaming_dense_encode_windows_errors_and_capacity(monkeypatch, window_mb, reserved):
+    """slzw_encode_batch_host_dense as one streaming launch: many windows (down to a handful of
+    streams each), rejected bytes, empty streams, per-stream code sizes, and a dense buffer that is
+    too small (SLZW_RC_NOMEM with the size needed, then the same call again with room)."""
+    import lzw_b200
+    monkeypatch.setenv("SLZW_HOST_WINDOW_MB", window_mb)
+    monkeypatch.setenv("SLZW_HOST_STREAM_SMS", reserved)
+    c = lzw_b200.Codec(0)
+    try:
+        rng = np.random.default_rng(2024)
+        n = 2500
+        cs = rng.integers(2, 9, size=n).astype(np.uint8)
+        streams = []
+        for i in range(n):
+            hi = (1 << int(cs[i])) - 1
+            length = int(rng.choice([0, 1, 3, 60, 900, 5000, 30000], p=[.03, .02, .02, .2, .43, .25, .05]))
+            s = T.make_stream(rng, T.KINDS[i % len(T.KINDS)], length, hi)
+            if hi < 255 and i % 89 == 7 and s.size > 4:
+                s[int(rng.integers(1, s.size))] = hi + 1  # UnexpectedCode
+            streams.append(s)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([s.size for s in streams])
+        buf = np.concatenate(streams)
+        p = O.gif(8)
+        slots = np.zeros(n + 1, dtype=np.uint64)
+        slots[1:] = np.cumsum([O.encode_bound(int(s.size)) for s in streams])
+        o_out, o_len, o_st, o_det = O.encode_batch(p, buf, off, slots, code_size=cs, threads=8)
+        assert int((o_st != 0).sum()) > 5
+        total = int(o_len.sum())
+        small = np.empty(total // 2, dtype=np.uint8)
+        with pytest.raises(RuntimeError):
+            c.encode_batch_dense(gp(p), buf, off, code_size=cs, out=small)
+        for _ in range(2):  # the second call reuses every buffer of the first
+            dense, doff, st, det = c.encode_batch_dense(gp(p), buf, off, code_size=cs)
+            assert np.array_equal(st, o_st) and np.array_equal(det, o_det)
+            assert np.array_equal(np.diff(doff), o_len) and dense.size == total
+            for i in range(n):
+                assert np.array_equal(dense[int(doff[i]):int(doff[i + 1])],
+                                      o_out[int(slots[i]):int(slots[i]) + int(o_len[i])]), i
     finally:
         c.close()
 
