@@ -174,8 +174,11 @@ SLZW_API int slzw_decode_batch_host(slzw_ctx* ctx, const slzw_params* params, co
  * out_dense[out_off[i] .. out_off[i+1]) (out_off has n+1 entries and is written by the call,
  * out_off[0] = 0, every stream rounded up to `align` bytes).  Worst-case slots live on the
  * device only; the compaction stage runs before the copy back, so only encoded bytes cross the
- * bus.  If out_off[n] would exceed out_cap nothing is copied, *needed (if not NULL) receives
- * the required size and SLZW_RC_NOMEM is returned.  This is what a TIFF/GIF writer wants:
+ * bus.  If out_off[n] would exceed out_cap the contents of out_dense are unspecified (streams
+ * that fit in front of the overflow may have been copied), *needed (if not NULL) receives the
+ * required size and SLZW_RC_NOMEM is returned.  The call keeps input + worst-case slots + dense
+ * output on the device (4.2 x the input bytes, context-owned, grow-only) and runs as one
+ * streaming launch fed by the copy engine; calls above 12 GiB of input are chunked.  This is what a TIFF/GIF writer wants:
  * strips back to back plus StripOffsets/StripByteCounts. */
 SLZW_API int slzw_encode_batch_host_dense(slzw_ctx* ctx, const slzw_params* params,
                                           const uint8_t* in, const uint64_t* in_off, uint64_t n,
