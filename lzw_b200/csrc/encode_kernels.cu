@@ -40,6 +40,12 @@
 #ifndef SLZW_INSERT_SYNC
 #define SLZW_INSERT_SYNC 1  // __syncwarp() between a shared-memory insert and the next bucket load
 #endif
+#ifndef SLZW_TILE
+#define SLZW_TILE 96   // input bytes per tile of the default configuration
+#endif
+#ifndef SLZW_SWARPS
+#define SLZW_SWARPS 12  // its warps with a shared-memory dictionary
+#endif
 #ifndef SLZW_HIT_REDUX
 #define SLZW_HIT_REDUX 1  // hit detection: one warp min-reduction (1) or ballot + find-first + shuffle (0)
 #endif
@@ -1006,7 +1012,7 @@ struct EncConfig {
 // per SM, one warp each.  Round 1 kept a second configuration (scalar speculative probes, 12 warps)
 // for batches with few streams; with the min-reduction lookups this one is faster there too
 // (config 4, 512 frames of 1 MiB: 148.7 against 171.9 ms), so every batch takes the same kernel.
-using Enc0 = EncConfig<96, 12, 16, 2>;
+using Enc0 = EncConfig<SLZW_TILE, SLZW_SWARPS, 16, 2>;
 // Latency variant (match_tile_lat): 12 warps per SM, shared-memory dictionaries only, for batches
 // that would leave most of Enc0's 28 warps per SM without a stream -- FIXED flavour only, where it
 // wins (1,776 text chunks of 64 KiB: 10.5 against 16.3 ms; once the table is full nothing but

@@ -250,6 +250,7 @@ struct slzw_ctx {
     struct DeferredChunk { uint64_t dev_off, bytes; };
     std::vector<DeferredChunk> deferred;
     uint64_t deferred_total = 0;
+    const uint8_t* deferred_base = nullptr;  // device buffer the deferred chunks live in
 };
 
 namespace {
@@ -741,7 +742,7 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
 int run_host_encode_stream(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
                            const uint64_t* in_off, uint64_t n, const uint8_t* code_size, uint64_t align,
                            uint8_t* out_dense, uint64_t out_cap, uint64_t* out_off, uint32_t* status,
-                           uint32_t* detail, uint64_t* needed) {
+                           uint32_t* detail, uint64_t* needed, bool deferred) {
     NvtxRange range("slzw encode batch, dense (streaming host pipeline)");
     EncPipe& ep = ctx->enc_pipe;
     StreamBufs& sb = ctx->sb;
@@ -898,9 +899,8 @@ int run_host_encode_stream(slzw_ctx* ctx, const slzw_params* params, const uint8
     CKS(cudaMemcpyAsync(sb.win_count.p, h_win_count, 4 * W, cudaMemcpyHostToDevice, ep.in), "H2D win_count");
     if (code_size) CKS(cudaMemcpyAsync(sb.cs.p, h_cs, n, cudaMemcpyHostToDevice, ep.in), "H2D code_size");
     CKS(cudaEventRecord(sb.ev_meta, ep.in), "cudaEventRecord");
-    for (size_t w = early; w < W; w++)
-        if ((rc = copy_window(w)) != SLZW_RC_OK) return fail(rc);
-    // ---- the one encode launch ----
+    // ---- the one encode launch (before the remaining copies are issued: from pageable memory
+    // every one of them holds the host until its bytes are staged) ----
     {
         std::lock_guard<std::mutex> lock(ctx->mu);
         DevBatch a;
@@ -934,6 +934,8 @@ int run_host_encode_stream(slzw_ctx* ctx, const slzw_params* params, const uint8
         ctx->launches += 1;
         ctx->last_encode_ws = -1;
     }
+    for (size_t w = early; w < W; w++)
+        if ((rc = copy_window(w)) != SLZW_RC_OK) return fail(rc);
     // ---- windows come back: compaction as soon as the kernel raises the flag, placement in order ----
     uint64_t hbase = 0;
     bool overflow = false;
@@ -974,10 +976,14 @@ int run_host_encode_stream(slzw_ctx* ctx, const slzw_params* params, const uint8
                 for (uint64_t i = 1; i <= m; i++) out_off[s0 + i] = hbase + doff[i];
                 memcpy(status + s0, h_status + s0, 4 * m);
                 memcpy(detail + s0, h_detail + s0, 4 * m);
-                if (hbase + tot > out_cap) overflow = true;
-                if (!overflow && tot)
-                    CKS(cudaMemcpyAsync(out_dense + hbase, (uint8_t*)sb.dense.p + dense_base(w), tot,
-                                        cudaMemcpyDeviceToHost, ep.dense), "D2H dense");
+                if (deferred) {  // the bytes stay in sb.dense until run_host_dense_finish
+                    ctx->deferred.push_back({dense_base(w), tot});
+                } else {
+                    if (hbase + tot > out_cap) overflow = true;
+                    if (!overflow && tot)
+                        CKS(cudaMemcpyAsync(out_dense + hbase, (uint8_t*)sb.dense.p + dense_base(w), tot,
+                                            cudaMemcpyDeviceToHost, ep.dense), "D2H dense");
+                }
                 tr.placed(w);
                 tr.mark(w, 2, ep.dense);
                 hbase += tot;
@@ -1007,6 +1013,10 @@ int run_host_encode_stream(slzw_ctx* ctx, const slzw_params* params, const uint8
     }
     tr.report("encode (dense, streaming)", in_off, wb);
     if (needed) *needed = hbase;
+    if (deferred) {
+        ctx->deferred_total = hbase;
+        ctx->deferred_base = (const uint8_t*)sb.dense.p;
+    }
     if (overflow) {
         snprintf(ctx->err, sizeof ctx->err, "dense output needs %llu bytes, capacity is %llu",
                  (unsigned long long)hbase, (unsigned long long)out_cap);
@@ -1057,10 +1067,10 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     if (!guard.ok) return fail_cuda(ctx, cudaGetLastError(), "cudaSetDevice");
     // one launch over the whole call when its buffers fit comfortably (4.2 x the input) and nothing
     // has to touch the input on the device first
-    if (ctx->enc_stream && !deferred && ctx->pred_row_bytes == 0 && n <= 0xFFFFFFFFull &&
+    if (ctx->enc_stream && ctx->pred_row_bytes == 0 && n <= 0xFFFFFFFFull &&
         in_off[n] - in_off[0] <= ctx->stream_max_bytes)
         return run_host_encode_stream(ctx, params, in, in_off, n, code_size, align, out_dense, out_cap, out_off,
-                                      status, detail, needed);
+                                      status, detail, needed, deferred);
     EncPipe& ep = ctx->enc_pipe;
     {
         std::lock_guard<std::mutex> lock(ctx->mu);
@@ -1227,7 +1237,10 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
 #undef CKP
     tr.report("encode (dense)", in_off, cb);
     if (needed) *needed = hbase;
-    if (deferred) ctx->deferred_total = hbase;
+    if (deferred) {
+        ctx->deferred_total = hbase;
+        ctx->deferred_base = (const uint8_t*)ctx->shard_dense.p;
+    }
     if (overflow) {
         snprintf(ctx->err, sizeof ctx->err, "dense output needs %llu bytes, capacity is %llu",
                  (unsigned long long)hbase, (unsigned long long)out_cap);
@@ -1253,7 +1266,7 @@ int run_host_dense_finish(slzw_ctx* ctx, uint8_t* dst, uint64_t cap) {
     for (size_t k = 0; k < ctx->deferred.size(); k++) {
         const auto& c = ctx->deferred[k];
         if (c.bytes)
-            CK(cudaMemcpyAsync(dst + at, (const uint8_t*)ctx->shard_dense.p + c.dev_off, c.bytes,
+            CK(cudaMemcpyAsync(dst + at, ctx->deferred_base + c.dev_off, c.bytes,
                                cudaMemcpyDeviceToHost, ctx->pipe[k % kPipe].stream),
                "D2H dense shard");
         at += c.bytes;
