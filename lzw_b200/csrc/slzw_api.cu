@@ -622,7 +622,9 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
         chunk_bounds(needs_out && op == Op::Decode ? b->out_off : b->in_off, n,
                      op == Op::Encode ? ctx->enc_chunk_bytes : ctx->dec_chunk_bytes,
                      ctx->chunk_min_streams ? (uint64_t)ctx->num_sms * (op == Op::Encode ? 28u : 32u) : 0u,
-                     op == Op::Encode ? ChunkShape::kTaper : ChunkShape::kRamp);
+                     op == Op::Encode ? (ctx->enc_shape == 1 ? ChunkShape::kHill : ChunkShape::kTaper)
+                                      : ChunkShape::kRamp,
+                     &ctx->hill);
     const size_t chunks = cb.size() - 1;
     // encode: pinned input is read in place (the decoder's input is small and its access pattern
     // re-reads tiles, it stays staged)
