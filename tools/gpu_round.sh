@@ -9,7 +9,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_ref
 python bench.py --workload config4 --steps 3 --warmup 3 > gpurun_out/r02_config4_1gpu.json 2> gpurun_out/r02_config4.err
 python bench.py --workload config5 --endian le --steps 3 --warmup 3 > gpurun_out/r02_config5_le_1gpu.json 2> gpurun_out/r02_config5.err
 python bench.py --workload config5 --endian be --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/r02_config5_be_1gpu.json 2>> gpurun_out/r02_config5.err
-python bench.py --single-process --gpus 1 --steps 3 --warmup 1 > gpurun_out/r02_single_process_1gpu.json 2> gpurun_out/r02_single_process.err
+python bench.py --single-process --gpus 1 --steps 3 --warmup 2 > gpurun_out/r02_single_process_1gpu.json 2> gpurun_out/r02_single_process.err
 for f in r02_bench_line r02_bench_reference r02_config4_1gpu r02_config5_le_1gpu r02_config5_be_1gpu r02_single_process_1gpu; do
   echo "== $f"; python - "$f" <<'P'
 import json, sys

@@ -14,7 +14,7 @@ $TR bench.py --gpus $N --steps 3 --warmup 3 --scaling strong > gpurun_out/r02_co
 $TR bench.py --gpus $N --steps 3 --warmup 3 --workload config4 > gpurun_out/r02_config4_${N}gpu.json 2>> gpurun_out/r02_scale_${N}gpu.err
 $TR bench.py --gpus $N --steps 3 --warmup 3 --workload config5 --endian le > gpurun_out/r02_config5_le_${N}gpu.json 2>> gpurun_out/r02_scale_${N}gpu.err
 $TR bench.py --gpus $N --steps 3 --warmup 3 --workload config5 --endian be --no-e2e > gpurun_out/r02_config5_be_${N}gpu.json 2>> gpurun_out/r02_scale_${N}gpu.err
-python bench.py --single-process --gpus $N --steps 3 --warmup 1 > gpurun_out/r02_single_process_${N}gpu.json 2>> gpurun_out/r02_scale_${N}gpu.err
+python bench.py --single-process --gpus $N --steps 3 --warmup 2 > gpurun_out/r02_single_process_${N}gpu.json 2>> gpurun_out/r02_scale_${N}gpu.err
 for f in r02_bench_${N}gpu r02_config3_strong_${N}gpu r02_config4_${N}gpu r02_config5_le_${N}gpu r02_config5_be_${N}gpu r02_single_process_${N}gpu; do
   echo "== $f"; python - "$f" <<'P'
 import json, sys
