@@ -727,6 +727,8 @@ int run_host(slzw_ctx* ctx, const slzw_params* params, const slzw_batch* b, Op o
     return SLZW_RC_OK;
 }
 
+constexpr int kStreamFallback = 1;  // run_host_encode_stream: not enough device memory, nothing was started
+
 // Streaming dense encode of a host batch: ONE encode launch for the whole call.
 //
 // The chunked pipeline below pays for its chunk boundaries: an encode CTA owns its SM until its 28
@@ -780,9 +782,19 @@ int run_host_encode_stream(slzw_ctx* ctx, const slzw_params* params, const uint8
                               up8(8 * (n + W)) + up8(4 * n) * 2 + 64;
     {
         std::lock_guard<std::mutex> lock(ctx->mu);
+        // the three large buffers first; a device that cannot hold them sends the call to the
+        // chunked pipeline.  Slots: slzw_encode_bound is below 1.5004 * len + 7, + 15 for alignment
+        const uint64_t slots_max = total + total / 2 + total / 2048 + 32 * n + 4096;
+        if (sb.in.reserve(total + 16) != cudaSuccess || sb.slots.reserve(slots_max + 16) != cudaSuccess ||
+            sb.dense.reserve(slots_max + align * n + 256) != cudaSuccess) {
+            cudaGetLastError();
+            sb.in.release();
+            sb.slots.release();
+            sb.dense.release();
+            return kStreamFallback;
+        }
         CK(sb.meta.reserve(meta_bytes), "cudaHostAlloc(meta)");
         CK(sb.flags.reserve(4 * (W + 1)), "cudaHostAlloc(flags)");
-        CK(sb.in.reserve(total + 16), "cudaMalloc(in)");
         CK(sb.in_off.reserve(8 * (n + 1)), "cudaMalloc(in_off)");
         CK(sb.out_off.reserve(8 * (n + 1)), "cudaMalloc(out_off)");
         CK(sb.out_len.reserve(8 * n), "cudaMalloc(out_len)");
@@ -1070,9 +1082,11 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     // one launch over the whole call when its buffers fit comfortably (4.2 x the input) and nothing
     // has to touch the input on the device first
     if (ctx->enc_stream && ctx->pred_row_bytes == 0 && n <= 0xFFFFFFFFull &&
-        in_off[n] - in_off[0] <= ctx->stream_max_bytes)
-        return run_host_encode_stream(ctx, params, in, in_off, n, code_size, align, out_dense, out_cap, out_off,
-                                      status, detail, needed, deferred);
+        in_off[n] - in_off[0] <= ctx->stream_max_bytes) {
+        const int rc = run_host_encode_stream(ctx, params, in, in_off, n, code_size, align, out_dense, out_cap,
+                                              out_off, status, detail, needed, deferred);
+        if (rc != kStreamFallback) return rc;
+    }
     EncPipe& ep = ctx->enc_pipe;
     {
         std::lock_guard<std::mutex> lock(ctx->mu);
