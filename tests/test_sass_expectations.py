@@ -67,3 +67,37 @@ def test_codec_kernels_do_not_spill():
         for name, lines in _functions(obj).items():
             if key in name:
                 assert not any(o.startswith(("LDL", "STL")) for o in _ops(lines)), name
+
+
+def test_lookup_loops_stay_within_their_instruction_budget():
+    """The encoder is bound by instruction issue; the four-lookup loop bodies of the MODE 0 loops
+    (the code nearly every input byte runs through) were 169 / 161 SASS instructions (tensor / shared
+    memory) at 71.3 ms per launch and are 156 / 141 at 65.5 ms (profiles/r02_encode_notes.md).  A
+    change that lets the compiler put instructions back fails here before it costs GPU time."""
+    funcs = _functions("encode_kernels.o")
+    name = next(n for n in funcs if "slzw_encode_kernelILi96ELi12ELi16ELi2ELb0ELb0" in n)
+    ins = []
+    for line in funcs[name]:
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", line)
+        if m:
+            ins.append((int(m.group(1), 16), m.group(2)))
+    index = {a: i for i, (a, _) in enumerate(ins)}
+    best = {"LDTM": None, "LDSM": None}
+    for i, (a, text) in enumerate(ins):
+        m = re.search(r"\bBRA(?:\.U)?\s+(?:\S+,\s*)?0x([0-9a-f]+)", text)
+        if not m or "BRA.DIV" in text:
+            continue
+        t = int(m.group(1), 16)
+        if t >= a or t not in index:
+            continue
+        body = [x for _, x in ins[index[t]:i + 1]]
+        for kind in best:
+            # four lookups + their four overflow reloads, one insert per lookup
+            loads = sum(1 for x in body if re.search(r"\b%s" % kind, x))
+            inserts = sum(1 for x in body if re.search(r"\bSTTM\b" if kind == "LDTM" else r"\bSTS\b", x))
+            if loads == 8 and (inserts == 4 if kind == "LDTM" else inserts == 8):
+                if best[kind] is None or len(body) < best[kind]:
+                    best[kind] = len(body)
+    assert best["LDTM"] is not None and best["LDSM"] is not None, best
+    assert best["LDTM"] <= 160, best
+    assert best["LDSM"] <= 146, best
