@@ -191,8 +191,8 @@ SLZW_API int slzw_encode_batch_host_dense(slzw_ctx* ctx, const slzw_params* para
  * slzw_multi_*).  _begin encodes and compacts; the encoded bytes stay on the device, out_off[n+1]
  * (relative to the first stream, out_off[0] = 0), status and detail come back and *total receives
  * out_off[n].  _finish copies the `total` bytes to out_dense (SLZW_RC_NOMEM if out_cap is smaller;
- * the bytes then stay available for another _finish).  A new _begin discards what an earlier one
- * left behind. */
+ * the bytes then stay available for another _finish).  A new _begin, or any other dense encode
+ * call on the same context, discards what an earlier _begin left behind. */
 SLZW_API int slzw_encode_batch_host_dense_begin(slzw_ctx* ctx, const slzw_params* params, const uint8_t* in,
                                        const uint64_t* in_off, uint64_t n, const uint8_t* code_size,
                                        uint64_t align, uint64_t* out_off, uint32_t* status,

@@ -1075,6 +1075,12 @@ int run_host_encode_dense(slzw_ctx* ctx, const slzw_params* params, const uint8_
     if (n == 0) return SLZW_RC_OK;
     HostCallGuard busy(ctx);
     if (!busy.ok) return SLZW_RC_INVALID;
+    // a one-phase dense encode reuses the device buffer that a streaming _begin left its bytes in:
+    // what that _begin left behind is discarded
+    if (!deferred && ctx->deferred_base && ctx->deferred_base == (const uint8_t*)ctx->sb.dense.p) {
+        ctx->deferred.clear();
+        ctx->deferred_total = 0;
+    }
     if (align == 0) align = 1;
     NvtxRange range("slzw encode batch, dense (host pipeline)");
     DeviceGuard guard(ctx->device);
