@@ -89,6 +89,15 @@ def test_two_phase_dense_encode():
         codec.encode_batch_dense_finish(small)  # SLZW_RC_NOMEM, the bytes stay available
     out = codec.encode_batch_dense_finish(np.empty(total, dtype=np.uint8))
     assert np.array_equal(out, dense)
+    # a second _finish has nothing left to copy; neither has one after a one-phase dense encode,
+    # which reuses the device buffer the _begin left its bytes in (slzw.h)
+    untouched = codec.encode_batch_dense_finish(np.full(total, 0xA5, dtype=np.uint8))
+    assert np.all(untouched == 0xA5)
+    codec.encode_batch_dense_begin(tiff_params(), buf, off)
+    again, _, _, _ = codec.encode_batch_dense(tiff_params(), buf, off)
+    assert np.array_equal(again, dense)
+    untouched = codec.encode_batch_dense_finish(np.full(total, 0xA5, dtype=np.uint8))
+    assert np.all(untouched == 0xA5)
     codec.close()
 
 
