@@ -148,7 +148,8 @@ SLZW_API uint64_t slzw_last_deferred(slzw_ctx* ctx, uint32_t* ids, uint64_t cap)
 /* Diagnostics: input bytes of the most recent encode call of this context by the kind of warp
  * that encoded them -- [0] one warp per stream, dictionary in tensor memory; [1] one warp per
  * stream, dictionary in shared memory; [2] one lane per stream, shared memory; [3] one lane per
- * stream, global memory (encode_kernels.cu).  Synchronises the device. */
+ * stream, global memory (encode_kernels.cu).  Synchronises the device.  Device-path and chunked
+ * host calls only: SLZW_RC_INVALID after a streaming dense encode (and before any encode call). */
 SLZW_API int slzw_last_encode_shares(slzw_ctx* ctx, uint64_t bytes[4]);
 
 /* ---- batched entry points (the hot path; new relative to the reference) ----------------- */
